@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline metric on BASELINE config 3.
+
+  metric   : Gsamples/s of 3D multiband wavelet noise (one sample = one output float, all its bands)
+  workload : WMultibandNoise dense volume 1024^3, bands 4..8 (q_b = 2 p 2^b, w_b = 2^-(b-4)), tile n=128 seed 12345,
+             z-slab sharded over the N ranks (strong scaling: the 1024^3 volume is fixed), one process per GPU.
+  step     : one pass of the hot path over the rank's slab (1024 x 1024 x 1024/N samples) into device memory.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every field).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = "wavelet-noise-in-ray-tracing_b200"
+sys.path.insert(0, ROOT)
+
+VOLUME = 1024
+TILE_N = 128
+SEED = 12345
+FLOP_PER_SAMPLE = 475.0          # 5 bands x 95 FLOP (separable form)
+OUT_BYTES_PER_SAMPLE = 4.0       # one float32 written to HBM per sample
+METRIC = "Gsamples/s 3D multiband wavelet noise"
+UNIT = "Gsamples/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def config3(wnsh):
+    ax = wnsh.lattice_axes_config3(VOLUME)
+    scale, w, post = wnsh.config3_bands(4, 8)
+    return ax, scale, w, post
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path (oracle/_ref when built, else the port)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(ax, scale, w, post, target_seconds, threads=0):
+    """Times the composed multiband loop over the reference's evaluate3D on a bounded slab.
+    Returns dict(value Gsamples/s, cores, kind, sample, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle, RefLib
+    if RefLib.available():
+        ref = RefLib()
+        noise = ref.noise(TILE_N, SEED).generate(3)
+        cores = ref.max_threads() if threads <= 0 else threads
+        run = lambda zs: noise.multiband3d_lattice(ax, ax, zs, scale, w, post, threads=cores)   # noqa: E731
+        kind = "reference"
+    else:
+        orc = Oracle()
+        tile = orc.generate_tile(TILE_N, SEED, 3)
+        cores = orc.max_threads() if threads <= 0 else threads
+        run = lambda zs: orc.multiband3d_lattice(tile, TILE_N, ax, ax, zs, scale, w, post, threads=cores)   # noqa: E731
+        kind = "port"
+    t0 = time.perf_counter()
+    run(ax[512:513])                                         # calibration: one 1024^2 slice
+    per_slice = time.perf_counter() - t0
+    nz = int(max(1, min(64, round(target_seconds / max(per_slice, 1e-6)))))
+    zs = ax[512:512 + nz]
+    t0 = time.perf_counter()
+    run(zs)
+    dt = time.perf_counter() - t0
+    samples = VOLUME * VOLUME * nz
+    return {"value": samples / dt / 1e9, "unit": UNIT, "cores": int(cores), "kind": kind,
+            "sample": f"{VOLUME}x{VOLUME}x{nz} slab of the 1024^3 volume (z index 512..), {dt:.2f} s", "seconds": dt,
+            "nz": nz, "run": run}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    wnsh_ax = (np.arange(VOLUME, dtype=np.float32) / np.float32(VOLUME)) * np.float32(4.0)
+    b = np.arange(4, 9)
+    scale = (2.0 * 2.0 ** b).astype(np.float32)
+    w = (2.0 ** -(b - 4).astype(np.float64)).astype(np.float32)
+    post = np.float32(1.0) / np.sqrt(np.float32((w * w).sum()) * np.float32(0.18402))
+    cal = cpu_reference_rate(wnsh_ax, scale, w, post, target_seconds=3.0)
+    run, nz = cal["run"], cal["nz"]
+    zs = wnsh_ax[512:512 + nz]
+    for _ in range(args.warmup):
+        run(zs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(zs)
+    dt = time.perf_counter() - t0
+    samples = VOLUME * VOLUME * nz * args.steps
+    value = samples / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "WMultibandNoise 1024^3 bands 4-8, tile n=128 seed 12345 (BASELINE config 3); "
+                               f"each step is a bounded {VOLUME}x{VOLUME}x{nz} slab on the host CPU",
+                   "tile_n": TILE_N, "bands": [4, 8]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cal["cores"], "kind": cal["kind"],
+                         "sample": f"{VOLUME}x{VOLUME}x{nz} slab per step x {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    wn = importlib.import_module(PKG)
+    wnsh = importlib.import_module(PKG + ".sharding")
+    torch.cuda.set_device(local_rank)
+    ctx = wn.Context(local_rank)
+    ctx.use_torch_stream()
+    ax, scale, w, post = config3(wnsh)
+
+    # --- tile: rank 0 builds (reference generator sequence on the host + GPU filter passes), one broadcast replicates it
+    noise = wn.WaveletNoise(TILE_N, SEED, ctx)
+    t0 = time.perf_counter()
+    wnsh.replicate_noise(noise, 3, lambda nz: nz.generateNoiseTile3D())
+    ctx.synchronize()
+    tile_total_ms = (time.perf_counter() - t0) * 1e3
+    tile_kernel_ms = ctx.last_kernel_ms if rank == 0 else None
+
+    zb, ze = wnsh.slab_range(VOLUME, rank, world)
+    zs = ax[zb:ze]
+    nz_local = ze - zb
+    samples_local = VOLUME * VOLUME * nz_local
+    out = torch.empty((nz_local, VOLUME, VOLUME), dtype=torch.float32, device=f"cuda:{local_rank}")
+
+    def step():
+        noise.multiband3D_lattice(ax, ax, zs, scale, w, float(post), mode=wn.WN_EVAL_FAST, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    elapsed_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    total_samples = VOLUME ** 3 * args.steps
+    value = total_samples / (elapsed_ms * 1e-3) / 1e9
+
+    # --- e2e: the public host-buffer call (axes H2D, result D2H into pinned host memory inside the timed region)
+    e2e_steps = min(args.steps, 5)
+    host_out = torch.empty((nz_local, VOLUME, VOLUME), dtype=torch.float32, pin_memory=True)
+
+    def e2e_step():
+        noise.multiband3D_lattice(ax, ax, zs, scale, w, float(post), mode=wn.WN_EVAL_FAST, out=host_out)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = VOLUME ** 3 * e2e_steps / float(t.item()) / 1e9
+    h2d_bytes = int((ax.nbytes * 2 + zs.nbytes) + scale.nbytes + w.nbytes)
+    d2h_bytes = int(samples_local * 4)
+    # sanity: the e2e result equals the device-resident result
+    same = bool(torch.equal(host_out[:1], out[:1].cpu()))
+    del host_out
+
+    if rank != 0:
+        return
+    hbm_peak, peak_src = peaks()
+    med_launch_ms = float(np.median(per_launch_ms))
+    achieved_gbs = samples_local * OUT_BYTES_PER_SAMPLE / (med_launch_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "k_mb3d_lattice (multiband lattice)",
+        "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+        "peak_source": peak_src, "traffic": None,
+        "algorithmic_bytes_per_launch": samples_local * OUT_BYTES_PER_SAMPLE + TILE_N ** 3 * 4,
+        "launch_ms": med_launch_ms,
+        "fp32": {"flop_per_sample": FLOP_PER_SAMPLE,
+                 "achieved_tflops": samples_local * FLOP_PER_SAMPLE / (med_launch_ms * 1e-3) / 1e12,
+                 "note": "SURVEY 8(d) algorithmic FLOP (5 bands x 95); the kernel is FP32/LSU-issue bound, not HBM bound"},
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cal = cpu_reference_rate(ax, scale, w, post, target_seconds=12.0)
+        cpu = {k: cal[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    # tile-gen ms at n=128 (second half of BASELINE's metric)
+    tg = wn.WaveletNoise(TILE_N, SEED, ctx)
+    t0 = time.perf_counter()
+    R = tg.gaussian_field(TILE_N ** 3)
+    fill_ms = (time.perf_counter() - t0) * 1e3
+    Rd = torch.from_numpy(R).cuda()
+    torch.cuda.synchronize()
+    tms = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        tg.generateNoiseTile3D(field=Rd)
+        b.record()
+        torch.cuda.synchronize()
+        tms.append(a.elapsed_time(b))
+    t0 = time.perf_counter()
+    tg.generateNoiseTile3D(field=R)
+    with_h2d_ms = (time.perf_counter() - t0) * 1e3
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "WMultibandNoise 1024^3 bands 4-8 weighted 2^-(b-4), tile n=128 seed 12345 "
+                               "(BASELINE config 3), z-slab sharded",
+                   "tile_n": TILE_N, "bands": [4, 8], "volume": [VOLUME] * 3, "slab_per_gpu": [VOLUME, VOLUME, nz_local],
+                   "parallelism": f"z-slab x{world}",
+                   "l2": "each step writes 4 GiB/N of fresh output (>> 126 MB L2); the 8 MiB tile is L2-resident by design"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "steps": e2e_steps, "matches_device_result": same},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "tile_gen_ms_n128": {"filters_device_only": float(np.median(tms)), "with_h2d": with_h2d_ms,
+                             "host_gaussian_fill": fill_ms, "first_build_incl_broadcast": tile_total_ms,
+                             "first_build_kernels": tile_kernel_ms},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,196 @@
+/*
+ * wn_b200.h -- C ABI of the B200-native wavelet-noise path (libwn_b200.so).
+ *
+ * The reference (Jason9339/Wavelet-Noise-in-ray-tracing) has no FFI layer: its boundary is the
+ * C++ class `WaveletNoise` (WaveletNoise.h:20-59), `PerlinNoise`/`perlin`
+ * (experient/PerlinNoise.hpp:9-61, perlin.h:14-91) and the `texture::value()` hook
+ * (texture.h:14-18).  This header is what a binding for that path calls; every entry point
+ * names the reference interface it replaces.  The drop-in host layers built on top of it are
+ *   - C++   : wavelet-noise-in-ray-tracing_b200/cpp/WaveletNoise.cpp (+ PerlinNoise.hpp, batch drivers)
+ *   - Python: wavelet-noise-in-ray-tracing_b200/ (ctypes mirror used by tests/ and bench.py)
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative WN_E* code on failure, and never throws;
+ *     wn_last_error() returns the message of the calling thread's last failure.
+ *   - there is NO CPU fallback: without a CUDA device wn_ctx_create fails with WN_ENODEVICE.
+ *   - one wn_ctx = one GPU + one stream; one host thread drives a context at a time.
+ *     Multi-GPU = one process (or context) per GPU; samples shard with no exchange.
+ *   - `space` says where the caller's sample buffers live:
+ *       WN_HOST   : host memory (pinned is faster).  The call copies in, computes, copies out and
+ *                   returns after the result is in `out` (large lattices are chunked so the D2H of
+ *                   one chunk overlaps the kernel of the next).
+ *       WN_DEVICE : device memory on the context's GPU.  Work is only enqueued on the context's
+ *                   stream; the caller synchronises (wn_ctx_synchronize or its own stream sync).
+ *     Small parameter arrays (coordinate axes, band scales, weights, normals when shared, perm
+ *     tables) are always HOST pointers and are copied at call time.
+ *   - tile layout: idx = x + n*y + n*n*z, float32 (WaveletNoise.cpp:154,163,172,209).
+ *   - lattice / grid output layout: out[i + nx*(j + ny*k)], float32 -- the `.raw` layout of
+ *     experient/main.cpp:28-34 for nz = 1.
+ */
+#ifndef WN_B200_H
+#define WN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WN_OK            0
+#define WN_EINVAL       -1   /* bad argument                                  */
+#define WN_ENODEVICE    -2   /* no CUDA device / wrong architecture           */
+#define WN_ECUDA        -3   /* a CUDA runtime call failed                    */
+#define WN_ENOMEM       -4
+#define WN_ESTATE       -5   /* e.g. evaluating a tile that was never built   */
+
+#define WN_HOST          0
+#define WN_DEVICE        1
+
+/* wn_tile_create flags */
+#define WN_TILE_DEFAULT      0u
+#define WN_TILE_ODD_OFFSET   1u   /* add the paper's odd-offset copy (Cook&DeRose App.1); the
+                                     reference omits it (WaveletNoise.cpp:179-182), default off */
+
+/* wn_multiband3d_lattice `mode` */
+#define WN_EVAL_FAST     0   /* separable, fused-multiply-add kernel (<= 1e-5 * tile range)      */
+#define WN_EVAL_EXACT    1   /* reference operation order, un-fused: bit-identical to the CPU     */
+
+typedef struct wn_ctx    wn_ctx;
+typedef struct wn_tile   wn_tile;
+typedef struct wn_perlin wn_perlin;
+typedef struct wn_rng    wn_rng;
+
+/* mirrors `struct DataStats` (WaveletNoise.h:11-18); count_nan_inf/energy are never written by
+ * the reference and are left 0 here as well. */
+typedef struct {
+    float     avg, var, min_val, max_val;
+    long long count_nan_inf;
+    float     energy;
+} wn_stats;
+
+/* ---- diagnostics -------------------------------------------------------------------------- */
+const char *wn_last_error(void);
+const char *wn_version(void);
+/* number of kernels this library launched since the context was created (bench.py gpu_launches) */
+uint64_t    wn_kernel_launches(const wn_ctx *ctx);
+/* CUDA-event time of the kernels enqueued by the most recent WN_HOST call on this context (ms) */
+float       wn_timing_last_ms(const wn_ctx *ctx);
+
+/* ---- context ------------------------------------------------------------------------------ */
+int  wn_ctx_create(int device /* -1 = current */, wn_ctx **out);
+int  wn_ctx_destroy(wn_ctx *ctx);
+int  wn_ctx_set_stream(wn_ctx *ctx, void *cuda_stream /* cudaStream_t, NULL = library's own */);
+int  wn_ctx_synchronize(wn_ctx *ctx);
+int  wn_ctx_device(const wn_ctx *ctx, int *device, int *sm_count);
+/* pinned host buffers for callers that want full-speed copies */
+int  wn_host_alloc(size_t bytes, void **out);
+int  wn_host_free(void *p);
+
+/* ---- host RNG: the reference's own generator objects ---------------------------------------
+ * replaces: the `std::mt19937 rng; std::normal_distribution<float> gaussianDist` members
+ * (WaveletNoise.h:47-48) and the fill loops WaveletNoise.cpp:74-77 / :146-147.  The state
+ * persists across calls so a second generate* continues the stream like the reference does. */
+int  wn_rng_create(unsigned seed, wn_rng **out);
+int  wn_rng_destroy(wn_rng *rng);
+int  wn_rng_fill_gaussian(wn_rng *rng, float *out_host, size_t count);
+/* std::shuffle(iota(256), std::mt19937(seed)) duplicated to 512 ints: the constructors
+ * PerlinNoise.hpp:29-34 and perlin.h:34-39 */
+int  wn_perlin_make_perm(unsigned seed, int32_t perm512_host[512]);
+
+/* ---- tile construction ----------------------------------------------------------------------
+ * replaces: WaveletNoise::WaveletNoise (cpp:20-26), generateNoiseTile2D (cpp:69-108),
+ * generateNoiseTile3D (cpp:142-183), getNoiseCoefficients / getTileSize (cpp:290-291). */
+int  wn_adjust_tile_size(int n);                       /* odd n -> n+1, the ctor rule cpp:22-25 */
+int  wn_tile_create(wn_ctx *ctx, int n, int dims /* 2|3 */, unsigned flags, wn_tile **out);
+int  wn_tile_destroy(wn_tile *tile);
+int  wn_tile_info(const wn_tile *tile, int *n, int *dims, size_t *count, int *built);
+/* R = the Gaussian field (n^dims floats, memory order).  Runs the separable down/up passes and the
+ * subtraction on the GPU.  Arithmetic is un-fused and in the reference's summation order, so the
+ * tile is bit-identical to the CPU one for the same R. */
+int  wn_tile_build_from_gaussian(wn_tile *tile, const float *R, int space);
+/* device-side fill: MT19937 + libstdc++'s polar method on the GPU, same accept/reject sequence
+ * (so every variate lands in the same cell); float values differ from glibc logf by <= 1 ulp. */
+int  wn_tile_build_seeded(wn_tile *tile, unsigned seed);
+/* adopt finished coefficients (e.g. a copy of a WaveletNoise object, or a cached tile) */
+int  wn_tile_upload(wn_tile *tile, const float *N, int space);
+int  wn_tile_download(const wn_tile *tile, float *out, int space);
+int  wn_tile_device_ptr(const wn_tile *tile, void **dptr);   /* for NCCL broadcast of the tile */
+int  wn_tile_mark_built(wn_tile *tile);                      /* after writing through the ptr  */
+
+/* ---- evaluation: scattered points -----------------------------------------------------------
+ * out[i] = evaluate*(p_i * pre_scale) * post_scale.
+ * replaces: WaveletNoise::evaluate2D (cpp:111-140), evaluate3D (cpp:185-215),
+ * evaluate3DProjected (cpp:218-265) called in a loop; the scalar methods are count = 1.
+ * p is AoS (xy / xyz per point).  Reference operation order, bit-identical. */
+int  wn_eval2d_points(const wn_tile *tile, const float *p, size_t count,
+                      float pre_scale, float post_scale, float *out, int space);
+int  wn_eval3d_points(const wn_tile *tile, const float *p, size_t count,
+                      float pre_scale, float post_scale, float *out, int space);
+/* normals: 3 floats shared by all points (normal_is_shared=1, HOST pointer) or one xyz per point
+ * (normal_is_shared=0, same space as p).  Assumed unit length, like the reference. */
+int  wn_eval3d_projected_points(const wn_tile *tile, const float *p, const float *normals,
+                                int normal_is_shared, size_t count,
+                                float pre_scale, float post_scale, float *out, int space);
+/* out[i] = post_scale * sum_b weights[b] * evaluate3D(p_i * band_scale[b])   (paper App.2
+ * WMultibandNoise over the reference's evaluate3D; the reference itself only ever uses nbands=1:
+ * experient/main.cpp:45-58, texture.h:77-85). */
+int  wn_multiband3d_points(const wn_tile *tile, const float *p, size_t count,
+                           const float *band_scale, const float *weights, int nbands,
+                           float post_scale, float *out, int space);
+
+/* ---- evaluation: lattices (axis-aligned grids given by coordinate arrays) -------------------
+ * sample (i,j,k) = (xs[i], ys[j], zs[k]); the caller computes the axes with whatever float formula
+ * it uses (the reference: u = (float(x)/size)*4.0f, experient/main.cpp:20-21), so coordinates are
+ * bit-identical to the CPU loop.  replaces the per-pixel loops experient/main.cpp:18-30, :45-58. */
+int  wn_eval2d_lattice(const wn_tile *tile, const float *xs, int nx, const float *ys, int ny,
+                       float pre_scale, float post_scale, float *out, int space);
+int  wn_multiband3d_lattice(const wn_tile *tile,
+                            const float *xs, int nx, const float *ys, int ny, const float *zs, int nz,
+                            const float *band_scale, const float *weights, int nbands,
+                            float post_scale, int mode, float *out, int space);
+
+/* ---- evaluation: affine grids ----------------------------------------------------------------
+ * sample (i,j) = origin + us[i]*e1 + vs[j]*e2, each component evaluated as
+ * fadd(fadd(origin, fmul(us[i],e1)), fmul(vs[j],e2)) -- un-fused, fixed order -- then * pre_scale.
+ * replaces the loop experient/main.cpp:74-87 (and generalises it to oblique planes). */
+int  wn_eval3d_projected_grid(const wn_tile *tile, const float origin[3],
+                              const float e1[3], const float *us, int nu,
+                              const float e2[3], const float *vs, int nv,
+                              const float normal[3], float pre_scale, float post_scale,
+                              float *out, int space);
+int  wn_eval3d_grid(const wn_tile *tile, const float origin[3],
+                    const float e1[3], const float *us, int nu,
+                    const float e2[3], const float *vs, int nv,
+                    float pre_scale, float post_scale, float *out, int space);
+
+/* ---- Perlin reference noise -------------------------------------------------------------------
+ * replaces: PerlinNoise::noise / perlin::noise (PerlinNoise.hpp:36-60, perlin.h:42-72), double
+ * precision, un-fused, result narrowed to float on store (experient/main.cpp:104,122). */
+int  wn_perlin_create(wn_ctx *ctx, const int32_t perm512_host[512], wn_perlin **out);
+int  wn_perlin_destroy(wn_perlin *pn);
+int  wn_perlin_points(const wn_perlin *pn, const float *p, size_t count, float pre_scale,
+                      float *out, int space);
+int  wn_perlin_lattice(const wn_perlin *pn, const float *xs, int nx, const float *ys, int ny,
+                       const float *zs, int nz, float *out, int space);
+int  wn_perlin_grid(const wn_perlin *pn, const float origin[3],
+                    const float e1[3], const float *us, int nu,
+                    const float e2[3], const float *vs, int nv,
+                    float pre_scale, float *out, int space);
+
+/* ---- texture hooks (batched) ------------------------------------------------------------------
+ * grey[i] = the value wavelet_texture::value / noise_texture::value (texture.h:67-107, :37-43)
+ * returns in each colour channel for hit point p_i (xyz float, as stored in vec3). */
+int  wn_wavelet_texture_values(const wn_tile *tile3d, const float *p, size_t count,
+                               double scale, int octave, float *grey, int space);
+int  wn_perlin_texture_values(const wn_perlin *pn, const float *p, size_t count,
+                              double scale, int octave, float *grey, int space);
+
+/* ---- statistics --------------------------------------------------------------------------------
+ * replaces: WaveletNoise::calculateStats (cpp:268-288) without the printing (the host layer prints). */
+int  wn_stats_compute(wn_ctx *ctx, const float *data, size_t count, int space, wn_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WN_B200_H */

@@ -1,0 +1,76 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports exactly what include/wn_b200.h
+declares, and refuses to work without a GPU (no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import wnpkg
+
+ROOT = wnpkg.ROOT
+HEADER = os.path.join(ROOT, "include", "wn_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(wn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = wnpkg.load_sub("_lib")
+    names = header_functions()
+    assert len(names) >= 35
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (wn_[a-z0-9_]+)$", out, flags=re.M))
+    missing = [n for n in names if n not in exported]
+    assert not missing, f"declared in wn_b200.h but not exported: {missing}"
+    extra = sorted(exported - set(names))
+    assert not extra, f"exported but not declared in wn_b200.h: {extra}"
+    # the Python binding covers the same set
+    assert sorted(lib.SIGNATURES) == names
+
+
+def test_no_oracle_in_product_path():
+    """The product package must never import or link the oracle."""
+    pkg_dir = os.path.join(ROOT, wnpkg.PKG)
+    for dirpath, _, files in os.walk(pkg_dir):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp", ".cuh", ".sh")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "wn_oracle" not in text and "libwnref" not in text and "oracle_lib" not in text, f
+    lib = wnpkg.load_sub("_lib")
+    ldd = subprocess.run(["ldd", lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "wnref" not in ldd
+
+
+def test_pure_host_helpers_and_argument_errors():
+    lib = wnpkg.load_sub("_lib").lib
+    assert lib.wn_adjust_tile_size(127) == 128 and lib.wn_adjust_tile_size(128) == 128
+    assert b"sm_100a" in lib.wn_version()
+    perm = (C.c_int32 * 512)()
+    assert lib.wn_perlin_make_perm(12345, perm) == 0
+    assert list(perm[:8]) == [48, 218, 61, 238, 202, 125, 107, 148]
+    assert list(perm[256:264]) == list(perm[:8])
+    rng = C.c_void_p()
+    assert lib.wn_rng_create(12345, C.byref(rng)) == 0
+    buf = (C.c_float * 8)()
+    assert lib.wn_rng_fill_gaussian(rng, buf, 8) == 0
+    got = [C.c_uint32.from_buffer(C.c_float(v)).value for v in buf]
+    assert got == [0xbf492c2c, 0xbec80f26, 0x3f0763bd, 0xbef51152, 0x3f96f80f, 0x401f5e2b, 0x3f0491d6, 0x3dde10bb]
+    lib.wn_rng_destroy(rng)
+    assert lib.wn_ctx_create(0, None) == -1 and b"NULL" in lib.wn_last_error()
+
+
+def test_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    wn = wnpkg.load()
+    with pytest.raises(wn.WnError) as e:
+        wn.Context()
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)

@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (via the ctypes host mirror), against the
+CPU oracle, the reference-generated vectors and the reference's 15 shipped golden images.
+
+Bars (stated here, enforced below):
+  * integer / index work and every reference-order kernel (tile construction, points, projected,
+    Perlin, texture hooks, exact lattice): BIT-EXACT vs the oracle.
+  * the FAST multiband lattice kernel (separable, FMA): max |err| <= 1e-5 * (tile max - tile min)
+    per unit of band weight (north_star tolerance).
+"""
+import numpy as np
+import pytest
+
+import experiment_cases as ex
+import wnpkg
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_bits(got, want, what=""):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape or got.size == want.size, what
+    bad = bits(got).ravel() != bits(want).ravel()
+    if bad.any():
+        i = int(np.flatnonzero(bad)[0])
+        raise AssertionError(f"{what}: {int(bad.sum())}/{bad.size} floats differ; first at {i}: "
+                             f"{got.ravel()[i]!r} vs {want.ravel()[i]!r}")
+
+
+@pytest.fixture(scope="module")
+def wn():
+    return wnpkg.load()
+
+
+@pytest.fixture(scope="module")
+def gpu_tiles(wn):
+    t2 = wn.WaveletNoise(128, 12345)
+    t2.generateNoiseTile2D()
+    t3 = wn.WaveletNoise(128, 12345)
+    t3.generateNoiseTile3D()
+    return {2: t2, 3: t3}
+
+
+# ---------------------------------------------------------------------------------------------
+# tile construction
+# ---------------------------------------------------------------------------------------------
+def test_tile_n128_bit_exact(gpu_tiles, tiles128):
+    assert_bits(gpu_tiles[3].getNoiseCoefficients(), tiles128[3], "3D tile n=128")
+    assert_bits(gpu_tiles[2].getNoiseCoefficients(), tiles128[2], "2D tile n=128")
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 30, 31, 34, 62, 100, 256])
+@pytest.mark.parametrize("dims", [2, 3])
+def test_tile_sizes_bit_exact(wn, oracle, n, dims):
+    if dims == 3 and n == 256:
+        pytest.skip("n=256 3D covered by test_tile_n256_3d")
+    w = wn.WaveletNoise(n, 1000 + n)
+    (w.generateNoiseTile3D if dims == 3 else w.generateNoiseTile2D)()
+    want = oracle.generate_tile(n, 1000 + n, dims)
+    assert w.getTileSize() == oracle.adjust(n)
+    assert_bits(w.getNoiseCoefficients(), want, f"tile n={n} dims={dims}")
+
+
+def test_tile_n256_3d(wn, oracle):
+    # BASELINE config 2's second size.  Same Gaussian field on both sides (oracle fill), filters on the GPU.
+    g = oracle.rng(12345)
+    R = oracle.gaussian_fill(g, 256 ** 3)
+    w = wn.WaveletNoise(256, 12345)
+    w.generateNoiseTile3D(field=R)
+    oracle.set_threads(0)
+    want = oracle.tile_from_field(R, 256, 3)
+    assert_bits(w.getNoiseCoefficients(), want, "3D tile n=256")
+    # and the library's own host fill draws the same field
+    w2 = wn.WaveletNoise(256, 12345)
+    assert_bits(w2.gaussian_field(1 << 20), R[:1 << 20], "gaussian field")
+
+
+def test_second_generate_continues_rng_stream(wn, oracle):
+    w = wn.WaveletNoise(16, 99)
+    w.generateNoiseTile2D()
+    w.generateNoiseTile3D()
+    g = oracle.rng(99)
+    oracle.generate_tile(16, 99, 2, g)
+    assert_bits(w.getNoiseCoefficients(), oracle.generate_tile(16, 99, 3, g), "second generate")
+
+
+def test_seeded_build_and_device_field(wn, oracle, tiles128):
+    import torch
+    w = wn.WaveletNoise(128, 12345)
+    w.generate_seeded(3)
+    got = w.getNoiseCoefficients()
+    rng = tiles128[3].max() - tiles128[3].min()
+    assert np.abs(got - tiles128[3]).max() <= 1e-5 * rng
+    # device-resident Gaussian field in, nothing crosses PCIe
+    R = oracle.gaussian_fill(oracle.rng(5), 32 ** 3)
+    w = wn.WaveletNoise(32, 5)
+    w.generateNoiseTile3D(field=torch.from_numpy(R).cuda())
+    w.ctx.synchronize()
+    assert_bits(w.getNoiseCoefficients(), oracle.tile_from_field(R, 32, 3), "device field")
+
+
+def test_odd_offset_flag_matches_paper_restatement(wn, oracle):
+    R = oracle.gaussian_fill(oracle.rng(7), 20 ** 3)
+    w = wn.WaveletNoise(20, 7, flags=wn.WN_TILE_ODD_OFFSET)
+    w.generateNoiseTile3D(field=R)
+    want = oracle.odd_offset3d(oracle.tile_from_field(R, 20, 3), 20)
+    assert_bits(w.getNoiseCoefficients(), want, "odd-offset tile")
+
+
+def test_stats(wn, oracle, gpu_tiles, tiles128):
+    st = gpu_tiles[3].ctx.stats(tiles128[3])
+    avg, var, mn, mx = oracle.stats(tiles128[3])
+    assert st.min_val == mn and st.max_val == mx
+    assert abs(st.var - var) <= 2e-7 and abs(st.avg - avg) <= 1e-9
+    empty = gpu_tiles[3].ctx.stats(np.empty(0, np.float32))
+    assert empty.avg == 0 and empty.var == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# the 15 golden images (config 1) -- through the experiment drop-in
+# ---------------------------------------------------------------------------------------------
+def test_experiment_driver_reproduces_all_15_goldens_bit_exact(wn, golden_dir, tmp_path):
+    exp = wnpkg.load_sub("experiment")
+    images = exp.main(str(tmp_path))
+    assert len(images) == 15
+    for octave in ex.OCTAVES:
+        for kind in ("w2d", "w3d", "wproj", "p2d", "p3d"):
+            name = ex.raw_name(kind, octave)
+            want = ex.load_raw(golden_dir, kind, octave)
+            got = np.fromfile(tmp_path / name, dtype="<f4").reshape(256, 256)
+            assert_bits(got, want, name)
+
+
+# ---------------------------------------------------------------------------------------------
+# evaluators vs reference-generated vectors and the oracle
+# ---------------------------------------------------------------------------------------------
+def test_points_match_reference_vectors(wn, gpu_tiles, ref_vectors):
+    rv = ref_vectors
+    pts = rv["pts3"]
+    assert_bits(gpu_tiles[3].evaluate3D_points(pts), rv["eval3d"], "evaluate3D")
+    assert_bits(gpu_tiles[2].evaluate2D_points(pts[:, :2].copy()), rv["eval2d"], "evaluate2D")
+    sel = slice(0, 2048)
+    assert_bits(gpu_tiles[3].evaluate3DProjected_points(pts[sel], rv["normals"][sel]), rv["proj_pernormal"], "proj/normal")
+    assert_bits(gpu_tiles[3].evaluate3DProjected_points(pts[sel], rv["nshared"]), rv["proj_shared"], "proj shared")
+    for seed in (12345, 5489):
+        assert_bits(wn.PerlinNoise(seed).noise_points(pts[:5376]), rv[f"perlin_{seed}"], f"perlin {seed}")
+
+
+def test_non_pow2_tile_evaluation(wn, oracle, ref_vectors):
+    rv = ref_vectors
+    w = wn.WaveletNoise(30, 807)
+    w.generateNoiseTile3D()
+    assert_bits(w.evaluate3D_points(rv["pts3"]), rv["eval3d_n30"], "evaluate3D n=30")
+    assert_bits(w.evaluate3DProjected_points(rv["pts3"][:512], rv["nshared"]), rv["proj_n30"], "projected n=30")
+
+
+def test_scalar_api_and_empty_tile(wn, oracle, gpu_tiles, tiles128):
+    p = [3.25, -7.5, 100.125]
+    assert gpu_tiles[3].evaluate3D(p) == oracle.eval3d(tiles128[3], 128, p)
+    assert gpu_tiles[2].evaluate2D(p[:2]) == oracle.eval2d(tiles128[2], 128, p[:2])
+    assert gpu_tiles[3].evaluate3DProjected(p, [.6, 0, .8]) == oracle.eval3d_projected(tiles128[3], 128, p, [.6, 0, .8])
+    fresh = wn.WaveletNoise(128, 1)
+    assert fresh.evaluate3D(p) == 0.0 and fresh.evaluate2D(p[:2]) == 0.0 and fresh.getNoiseCoefficients().size == 0
+    assert gpu_tiles[3].evaluate3D_points(np.empty((0, 3), np.float32)).size == 0
+    with pytest.raises(wn.WnError):
+        gpu_tiles[2].evaluate3D_points(np.zeros((1, 3), np.float32))       # 2D tile, 3D evaluator
+
+
+def test_texture_hooks(wn, ref_vectors):
+    rv = ref_vectors
+    tp = rv["tex_pts"]
+    wt = wn.wavelet_texture(1.0, 4, True)
+    assert_bits(wt.values(tp), rv["tex_wavelet_s1_o4"], "wavelet_texture s1 o4")
+    assert wt.value(0, 0, tp[0])[0] == rv["tex_wavelet_s1_o4"][0]
+    wt2 = wn.wavelet_texture(0.37, 3, True)
+    assert_bits(wt2.values(tp), rv["tex_wavelet_s0.37_o3"], "wavelet_texture s.37 o3")
+    assert_bits(wn.noise_texture(1.0, 4).values(tp), rv["tex_perlin_s1_o4"], "noise_texture s1 o4")
+    assert_bits(wn.noise_texture(0.37, 5).values(tp), rv["tex_perlin_s0.37_o5"], "noise_texture s.37 o5")
+
+
+def test_device_buffers_equal_host_buffers(wn, gpu_tiles, ref_vectors):
+    import torch
+    gpu_tiles[3].ctx.use_torch_stream()
+    try:
+        pts = torch.from_numpy(ref_vectors["pts3"]).cuda()
+        out = gpu_tiles[3].evaluate3D_points(pts)
+        assert out.is_cuda
+        assert_bits(out.cpu().numpy(), ref_vectors["eval3d"], "device-space evaluate3D")
+    finally:
+        gpu_tiles[3].ctx.set_stream(None)
+
+
+# ---------------------------------------------------------------------------------------------
+# multiband lattice (config 3) and affine grids (config 4)
+# ---------------------------------------------------------------------------------------------
+BANDS = np.array([2.0 * 2 ** b for b in range(4, 9)], np.float32)          # q_b = 2 p 2^b
+WEIGHTS = np.array([2.0 ** -(b - 4) for b in range(4, 9)], np.float32)
+POST = np.float32(1.0 / np.sqrt(np.float32((WEIGHTS * WEIGHTS).sum()) * np.float32(0.18402)))
+
+
+def lattice_axis(idx, size=1024):
+    return (np.asarray(idx, np.float32) / np.float32(size)) * np.float32(4.0)
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_multiband_lattice_subvolumes(wn, oracle, gpu_tiles, tiles128, mode):
+    rs = np.random.RandomState(3)
+    rng = float(tiles128[3].max() - tiles128[3].min())
+    tol = 1e-5 * rng * float(WEIGHTS.sum()) * float(POST)
+    for trial in range(6):
+        x0, y0, z0 = rs.randint(0, 1024 - 40, 3)
+        nx, ny, nz = (40, 33, 9) if trial % 2 else (37, 16, 12)
+        xs, ys, zs = (lattice_axis(np.arange(a, a + m)) for a, m in ((x0, nx), (y0, ny), (z0, nz)))
+        want = oracle.multiband3d_lattice(tiles128[3], 128, xs, ys, zs, BANDS, WEIGHTS, POST)
+        got = gpu_tiles[3].multiband3D_lattice(xs, ys, zs, BANDS, WEIGHTS, float(POST),
+                                               mode=wn.WN_EVAL_EXACT if mode == "exact" else wn.WN_EVAL_FAST)
+        if mode == "exact":
+            assert_bits(got, want, "exact multiband lattice")
+        else:
+            err = np.abs(got - want).max()
+            assert err <= tol, (err, tol)
+
+
+def test_multiband_lattice_irregular_axes_fast(wn, oracle, gpu_tiles, tiles128):
+    # non-uniform, non-monotone, negative and large coordinates; ragged sizes; single band
+    rs = np.random.RandomState(11)
+    xs = np.concatenate([rs.uniform(-50, 50, 77), [0.0, 0.5, -0.5, 127.5, 128.0, 1e4]]).astype(np.float32)
+    ys = rs.uniform(-3, 3, 19).astype(np.float32)
+    zs = np.sort(rs.uniform(-10, 300, 7)).astype(np.float32)
+    rng = float(tiles128[3].max() - tiles128[3].min())
+    for bs, w in (([1.0], [1.0]), ([1.0, 2.0, 4.0], [1.0, 0.5, 0.25])):
+        want = oracle.multiband3d_lattice(tiles128[3], 128, xs, ys, zs, bs, w, 1.0)
+        got = gpu_tiles[3].multiband3D_lattice(xs, ys, zs, bs, w, 1.0)
+        assert np.abs(got - want).max() <= 1e-5 * rng * sum(w)
+    assert gpu_tiles[3].multiband3D_lattice(xs, ys, np.empty(0, np.float32), [1.0], [1.0]).size == 0
+
+
+def test_multiband_full_size_properties(wn, oracle, gpu_tiles, tiles128):
+    """Config 3 at full 1024^2 x 8 slab size (device output): periodicity and oracle spot checks."""
+    import torch
+    t = gpu_tiles[3]
+    ax = lattice_axis(np.arange(1024))
+    zs = lattice_axis(np.arange(512, 520))
+    out = t.multiband3D_lattice(ax, ax, zs, BANDS, WEIGHTS, float(POST), device_out=True)
+    t.ctx.synchronize()
+    out = out.cpu().numpy()
+    rs = np.random.RandomState(5)
+    idx = rs.randint(0, 1024, (4096, 2))
+    kz = rs.randint(0, 8, 4096)
+    pts = np.stack([ax[idx[:, 0]], ax[idx[:, 1]], zs[kz]], -1)
+    want = oracle.multiband3d_points(tiles128[3], 128, pts, BANDS, WEIGHTS, POST)
+    rng = float(tiles128[3].max() - tiles128[3].min())
+    assert np.abs(out[kz, idx[:, 1], idx[:, 0]] - want).max() <= 1e-5 * rng * float(WEIGHTS.sum()) * float(POST)
+    # single band 4 over one full period (1024 samples = 128 cells): mean of N over a period ~ tile mean
+    one = t.multiband3D_lattice(ax, ax, zs[:1], BANDS[:1], [1.0], 1.0)
+    assert abs(float(one.mean())) < 0.05
+
+
+def test_projected_and_perlin_affine_grid_config4(wn, oracle, gpu_tiles, tiles128):
+    """Config 4 on a 96x80 window of the 8192^2 plane, oblique basis; coordinates are built un-fused on both sides."""
+    f = np.float32
+    nrm = (np.array([1, 2, 3], np.float64) / np.sqrt(14.0)).astype(f)
+    e1 = (np.array([2, -1, 0], np.float64) / np.sqrt(5.0)).astype(f)
+    e2 = (np.array([3, 6, -5], np.float64) / np.sqrt(70.0)).astype(f)
+    origin = np.array([0, 0, 1], f)
+    us = (np.arange(4000, 4096, dtype=f) / f(8192)) * f(4)
+    vs = (np.arange(100, 180, dtype=f) / f(8192)) * f(4)
+    pre = f(2.0 * 2 ** 4)
+    inv = f(1.0) / np.sqrt(f(0.296))
+    got = gpu_tiles[3].evaluate3DProjected_grid(origin, e1, us, e2, vs, nrm, float(pre), float(inv))
+    # same coordinate formula in numpy float32: ((o + u*e1) + v*e2) * pre
+    U, V = np.meshgrid(us, vs)
+    P = ((origin[None, None, :] + U[..., None] * e1) + V[..., None] * e2).astype(f) * pre
+    want = oracle.eval3d_projected_points(tiles128[3], 128, P.reshape(-1, 3), nrm, 1.0, inv).reshape(80, 96)
+    assert_bits(got, want, "projected affine grid")
+    got3 = gpu_tiles[3].evaluate3D_grid(origin, e1, us, e2, vs, float(pre), 1.0)
+    assert_bits(got3, oracle.eval3d_points(tiles128[3], 128, P.reshape(-1, 3)).reshape(80, 96), "evaluate3D affine grid")
+    pn = wn.PerlinNoise(12345)
+    gp = pn.noise_grid(origin, e1, us, e2, vs, float(f(2.0 ** 4)))
+    P4 = ((origin[None, None, :] + U[..., None] * e1) + V[..., None] * e2).astype(f) * f(2.0 ** 4)
+    assert_bits(gp, oracle.perlin_points(oracle.perlin_perm(12345), P4.reshape(-1, 3)).reshape(80, 96), "perlin affine grid")
+
+
+def test_large_host_call_is_chunked_consistently(wn, gpu_tiles):
+    """A WN_HOST lattice larger than one staging chunk equals the same lattice computed in one device call."""
+    t = gpu_tiles[3]
+    ax = lattice_axis(np.arange(1024))
+    zs = lattice_axis(np.arange(0, 40))                    # 40 Mi samples > 32 Mi chunk
+    host = t.multiband3D_lattice(ax, ax, zs, BANDS[:2], WEIGHTS[:2], 1.0)
+    dev = t.multiband3D_lattice(ax, ax, zs, BANDS[:2], WEIGHTS[:2], 1.0, device_out=True)
+    t.ctx.synchronize()
+    assert_bits(host, dev.cpu().numpy(), "chunked host vs device")

@@ -1,0 +1,23 @@
+#!/usr/bin/env bash
+# Builds libwn_b200.so (sm_100a only) next to this script's parent package directory.
+#   exact kernels  : -fmad=false  (reference operation order, un-fused)
+#   fast kernels   : FMA allowed
+# Host code is compiled without -march / with -ffp-contract=off so the libstdc++ polar method keeps
+# the reference's accept/reject sequence.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="${HERE}/.."
+BUILD="${HERE}/build"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-ffp-contract=off -ccbin /usr/bin/g++ ${ARCH}"
+mkdir -p "${BUILD}"
+PTXAS_V="${WN_PTXAS_V:+-Xptxas -v}"
+${NVCC} ${COMMON} ${PTXAS_V} -fmad=false -c "${HERE}/wn_tilegen.cu"        -o "${BUILD}/wn_tilegen.o"
+${NVCC} ${COMMON} ${PTXAS_V} -fmad=false -c "${HERE}/wn_eval_exact.cu"     -o "${BUILD}/wn_eval_exact.o"
+${NVCC} ${COMMON} ${PTXAS_V}             -c "${HERE}/wn_multiband_fast.cu" -o "${BUILD}/wn_multiband_fast.o"
+${NVCC} ${COMMON}               -fmad=false -c "${HERE}/wn_capi.cu"         -o "${BUILD}/wn_capi.o"
+${NVCC} ${ARCH} -shared -ccbin /usr/bin/g++ -o "${OUT}/libwn_b200.so" \
+    "${BUILD}/wn_tilegen.o" "${BUILD}/wn_eval_exact.o" "${BUILD}/wn_multiband_fast.o" "${BUILD}/wn_capi.o" \
+    -cudart static
+echo "built ${OUT}/libwn_b200.so"

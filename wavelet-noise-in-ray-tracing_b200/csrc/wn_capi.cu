@@ -1,0 +1,919 @@
+// wn_capi.cu -- the extern "C" surface of include/wn_b200.h: contexts, tiles, staging and launches.
+// No kernels live here (see wn_tilegen.cu, wn_eval_exact.cu, wn_multiband_fast.cu, wn_rng.cu).
+//
+// There is deliberately no CPU compute path in this file: every evaluation entry point ends in a kernel
+// launch, and wn_ctx_create fails when no sm_100 device is present.  The only host-side arithmetic is the
+// reference's own generator objects (std::mt19937 / std::normal_distribution<float> / std::shuffle), which
+// is exactly what the reference's constructors and fill loops run (WaveletNoise.h:47-48, cpp:74-77,146-147;
+// PerlinNoise.hpp:29-34).
+#include "../../include/wn_b200.h"
+#include "wn_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <random>
+#include <vector>
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int wn_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define WN_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return wn_fail(WN_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define WN_REQUIRE(cond, ...)                                                                      \
+    do {                                                                                           \
+        if (!(cond)) return wn_fail(WN_EINVAL, __VA_ARGS__);                                       \
+    } while (0)
+
+extern "C" const char *wn_last_error(void) { return g_err; }
+extern "C" const char *wn_version(void) { return "wn_b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+struct WnBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct wn_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;   // compute stream created by the library
+    cudaStream_t stream = nullptr;       // stream in use (own or caller's)
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    // double-buffered staging for WN_HOST calls
+    WnBuf in[2], aux[2], outb[2];
+    cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
+    WnBuf params;                        // coordinate axes etc. for the call in flight
+    WnBuf stats_partial;
+    std::vector<cudaEvent_t> tev;        // timing event pool (pairs)
+    size_t tev_used = 0;
+    float last_ms = 0.0f;
+    uint64_t launches = 0;
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int buf_reserve(WnBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return WN_OK;
+    if (b.p) WN_CUDA(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return wn_fail(WN_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return WN_OK;
+}
+
+extern "C" int wn_ctx_create(int device, wn_ctx **out)
+{
+    WN_REQUIRE(out, "wn_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return wn_fail(WN_ENODEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0) WN_CUDA(cudaGetDevice(&device));
+    WN_REQUIRE(device < count, "wn_ctx_create: device %d out of range (%d devices)", device, count);
+    cudaDeviceProp prop;
+    WN_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return wn_fail(WN_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                       prop.major, prop.minor);
+    DeviceGuard g(device);
+    wn_ctx *c = new (std::nothrow) wn_ctx();
+    if (!c) return wn_fail(WN_ENOMEM, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    WN_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    WN_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    WN_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (int i = 0; i < 2; ++i) {
+        WN_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        WN_CUDA(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+        WN_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+    }
+    *out = c;
+    return WN_OK;
+}
+
+extern "C" int wn_ctx_destroy(wn_ctx *c)
+{
+    if (!c) return WN_OK;
+    DeviceGuard g(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->in[i].p); cudaFree(c->aux[i].p); cudaFree(c->outb[i].p);
+        cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_k[i]); cudaEventDestroy(c->ev_out[i]);
+    }
+    cudaFree(c->params.p);
+    cudaFree(c->stats_partial.p);
+    for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->h2d); cudaStreamDestroy(c->d2h);
+    delete c;
+    return WN_OK;
+}
+
+extern "C" int wn_ctx_set_stream(wn_ctx *c, void *s)
+{
+    WN_REQUIRE(c, "wn_ctx_set_stream: ctx is NULL");
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return WN_OK;
+}
+
+extern "C" int wn_ctx_synchronize(wn_ctx *c)
+{
+    WN_REQUIRE(c, "wn_ctx_synchronize: ctx is NULL");
+    DeviceGuard g(c->device);
+    WN_CUDA(cudaStreamSynchronize(c->stream));
+    return WN_OK;
+}
+
+extern "C" int wn_ctx_device(const wn_ctx *c, int *device, int *sm_count)
+{
+    WN_REQUIRE(c, "wn_ctx_device: ctx is NULL");
+    if (device) *device = c->device;
+    if (sm_count) *sm_count = c->sm_count;
+    return WN_OK;
+}
+
+extern "C" uint64_t wn_kernel_launches(const wn_ctx *c) { return c ? c->launches : 0; }
+extern "C" float wn_timing_last_ms(const wn_ctx *c) { return c ? c->last_ms : 0.0f; }
+
+extern "C" int wn_host_alloc(size_t bytes, void **out)
+{
+    WN_REQUIRE(out, "wn_host_alloc: out is NULL");
+    WN_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return WN_OK;
+}
+extern "C" int wn_host_free(void *p)
+{
+    if (p) WN_CUDA(cudaFreeHost(p));
+    return WN_OK;
+}
+
+// timing helpers: pairs of events around kernel groups of a WN_HOST call
+static int timing_begin(wn_ctx *c) { c->tev_used = 0; c->last_ms = 0.0f; return WN_OK; }
+static int timing_mark(wn_ctx *c, cudaStream_t st)
+{
+    if (c->tev_used == c->tev.size()) {
+        cudaEvent_t e;
+        WN_CUDA(cudaEventCreate(&e));
+        c->tev.push_back(e);
+    }
+    WN_CUDA(cudaEventRecord(c->tev[c->tev_used++], st));
+    return WN_OK;
+}
+static int timing_end(wn_ctx *c)      // call after the streams have been synchronised
+{
+    float total = 0.0f;
+    for (size_t i = 0; i + 1 < c->tev_used; i += 2) {
+        float ms = 0.0f;
+        WN_CUDA(cudaEventElapsedTime(&ms, c->tev[i], c->tev[i + 1]));
+        total += ms;
+    }
+    c->last_ms = total;
+    return WN_OK;
+}
+
+// copy a small host parameter array into the context's device parameter block (stream ordered)
+struct ParamWriter {
+    wn_ctx *c;
+    size_t off = 0;
+    explicit ParamWriter(wn_ctx *ctx) : c(ctx) {}
+    int reserve(size_t bytes) { return buf_reserve(c->params, bytes + 1024); }
+    int put(const void *host, size_t bytes, const void **dptr)
+    {
+        off = (off + 255) & ~(size_t)255;
+        if (off + bytes > c->params.cap) return wn_fail(WN_EINVAL, "internal: parameter block overflow");
+        void *d = (char *)c->params.p + off;
+        // pageable source: the runtime stages it before returning, so the caller may reuse `host`
+        cudaError_t e = cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) return wn_fail(WN_ECUDA, "parameter upload failed: %s", cudaGetErrorString(e));
+        *dptr = d;
+        off += bytes;
+        return WN_OK;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// chunked HOST pipeline:  H2D(in, aux) -> kernel -> D2H(out), double buffered on three streams
+// ---------------------------------------------------------------------------------------------------
+struct ChunkIO {
+    const void *in = nullptr;  size_t in_item = 0;     // bytes per item (0 = no per-item input)
+    const void *aux = nullptr; size_t aux_item = 0;
+    void *out = nullptr;       size_t out_item = sizeof(float);
+};
+
+template <class Launch>
+static int run_chunked_host(wn_ctx *c, size_t total, size_t chunk, const ChunkIO &io, Launch launch)
+{
+    if (total == 0) return WN_OK;
+    if (chunk == 0 || chunk > total) chunk = total;
+    for (int s = 0; s < 2; ++s) {
+        if (io.in_item) { int r = buf_reserve(c->in[s], chunk * io.in_item); if (r) return r; }
+        if (io.aux_item) { int r = buf_reserve(c->aux[s], chunk * io.aux_item); if (r) return r; }
+        int r = buf_reserve(c->outb[s], chunk * io.out_item); if (r) return r;
+    }
+    // the parameter block was written on c->stream; the h2d stream needs no ordering with it.
+    timing_begin(c);
+    size_t nchunks = (total + chunk - 1) / chunk;
+    for (size_t ci = 0; ci < nchunks; ++ci) {
+        const int s = (int)(ci & 1);
+        const size_t first = ci * chunk, cnt = std::min(chunk, total - first);
+        const bool has_in = io.in_item || io.aux_item;
+        if (has_in) {
+            if (ci >= 2) WN_CUDA(cudaStreamWaitEvent(c->h2d, c->ev_k[s], 0));   // kernel ci-2 done with in[s]
+            if (io.in_item)
+                WN_CUDA(cudaMemcpyAsync(c->in[s].p, (const char *)io.in + first * io.in_item, cnt * io.in_item,
+                                        cudaMemcpyHostToDevice, c->h2d));
+            if (io.aux_item)
+                WN_CUDA(cudaMemcpyAsync(c->aux[s].p, (const char *)io.aux + first * io.aux_item, cnt * io.aux_item,
+                                        cudaMemcpyHostToDevice, c->h2d));
+            WN_CUDA(cudaEventRecord(c->ev_in[s], c->h2d));
+            WN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[s], 0));
+        }
+        if (ci >= 2) WN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_out[s], 0));    // D2H ci-2 done with outb[s]
+        int r = timing_mark(c, c->stream); if (r) return r;
+        int nl = launch(c->in[s].p, c->aux[s].p, (float *)c->outb[s].p, first, cnt, c->stream);
+        if (nl < 0) return wn_fail(WN_EINVAL, "kernel launch rejected the configuration");
+        c->launches += (uint64_t)nl;
+        WN_CUDA(cudaGetLastError());
+        r = timing_mark(c, c->stream); if (r) return r;
+        WN_CUDA(cudaEventRecord(c->ev_k[s], c->stream));
+        WN_CUDA(cudaStreamWaitEvent(c->d2h, c->ev_k[s], 0));
+        WN_CUDA(cudaMemcpyAsync((char *)io.out + first * io.out_item, c->outb[s].p, cnt * io.out_item,
+                                cudaMemcpyDeviceToHost, c->d2h));
+        WN_CUDA(cudaEventRecord(c->ev_out[s], c->d2h));
+    }
+    WN_CUDA(cudaStreamSynchronize(c->d2h));
+    WN_CUDA(cudaStreamSynchronize(c->stream));
+    return timing_end(c);
+}
+
+template <class Launch>
+static int run_device(wn_ctx *c, Launch launch)
+{
+    int nl = launch(c->stream);
+    if (nl < 0) return wn_fail(WN_EINVAL, "kernel launch rejected the configuration");
+    c->launches += (uint64_t)nl;
+    WN_CUDA(cudaGetLastError());
+    return WN_OK;
+}
+
+static const size_t kChunkSamples = (size_t)32 << 20;     // 32 Mi samples = 128 MiB of output per chunk
+
+// ---------------------------------------------------------------------------------------------------
+// host RNG (the reference's own generator objects)
+// ---------------------------------------------------------------------------------------------------
+struct wn_rng {
+    std::mt19937 engine;
+    std::normal_distribution<float> gauss;
+    explicit wn_rng(unsigned seed) : engine(seed), gauss(0.0f, 1.0f) {}
+};
+
+extern "C" int wn_rng_create(unsigned seed, wn_rng **out)
+{
+    WN_REQUIRE(out, "wn_rng_create: out is NULL");
+    *out = new (std::nothrow) wn_rng(seed);
+    return *out ? WN_OK : wn_fail(WN_ENOMEM, "out of host memory");
+}
+extern "C" int wn_rng_destroy(wn_rng *r) { delete r; return WN_OK; }
+extern "C" int wn_rng_fill_gaussian(wn_rng *r, float *out, size_t count)
+{
+    WN_REQUIRE(r && (out || !count), "wn_rng_fill_gaussian: NULL argument");
+    for (size_t i = 0; i < count; ++i) out[i] = r->gauss(r->engine);
+    return WN_OK;
+}
+extern "C" int wn_perlin_make_perm(unsigned seed, int32_t perm[512])
+{
+    WN_REQUIRE(perm, "wn_perlin_make_perm: perm is NULL");
+    std::vector<int> p(256);
+    std::iota(p.begin(), p.end(), 0);
+    std::shuffle(p.begin(), p.end(), std::mt19937(seed));
+    for (int i = 0; i < 256; ++i) perm[i] = perm[256 + i] = p[i];
+    return WN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tiles
+// ---------------------------------------------------------------------------------------------------
+struct wn_tile {
+    wn_ctx *ctx = nullptr;
+    int n = 0, dims = 0;
+    unsigned flags = 0;
+    size_t count = 0;
+    float *d = nullptr;
+    bool built = false;
+};
+
+static WnTileView tile_view(const wn_tile *t)
+{
+    WnTileView v;
+    v.N = t->d; v.n = t->n; v.pow2 = (t->n & (t->n - 1)) == 0;
+    return v;
+}
+
+extern "C" int wn_adjust_tile_size(int n) { return (n % 2 != 0) ? n + 1 : n; }
+
+extern "C" int wn_tile_create(wn_ctx *c, int n, int dims, unsigned flags, wn_tile **out)
+{
+    WN_REQUIRE(c && out, "wn_tile_create: NULL argument");
+    *out = nullptr;
+    WN_REQUIRE(dims == 2 || dims == 3, "wn_tile_create: dims must be 2 or 3 (got %d)", dims);
+    WN_REQUIRE(n >= 2, "wn_tile_create: tile size must be >= 2 (got %d)", n);
+    n = wn_adjust_tile_size(n);
+    WN_REQUIRE(dims == 3 ? n <= 1024 : n <= 16384, "wn_tile_create: tile size %d too large for %dD", n, dims);
+    WN_REQUIRE(!(flags & WN_TILE_ODD_OFFSET) || dims == 3, "wn_tile_create: WN_TILE_ODD_OFFSET needs a 3D tile");
+    DeviceGuard g(c->device);
+    wn_tile *t = new (std::nothrow) wn_tile();
+    if (!t) return wn_fail(WN_ENOMEM, "out of host memory");
+    t->ctx = c; t->n = n; t->dims = dims; t->flags = flags;
+    t->count = (dims == 3) ? (size_t)n * n * n : (size_t)n * n;
+    cudaError_t e = cudaMalloc(&t->d, t->count * sizeof(float));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete t;
+        return wn_fail(WN_ENOMEM, "cudaMalloc of the %d^%d tile failed: %s", n, dims, cudaGetErrorString(e));
+    }
+    *out = t;
+    return WN_OK;
+}
+
+extern "C" int wn_tile_destroy(wn_tile *t)
+{
+    if (!t) return WN_OK;
+    DeviceGuard g(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->d);
+    delete t;
+    return WN_OK;
+}
+
+extern "C" int wn_tile_info(const wn_tile *t, int *n, int *dims, size_t *count, int *built)
+{
+    WN_REQUIRE(t, "wn_tile_info: tile is NULL");
+    if (n) *n = t->n;
+    if (dims) *dims = t->dims;
+    if (count) *count = t->count;
+    if (built) *built = t->built ? 1 : 0;
+    return WN_OK;
+}
+
+// R (device) -> tile.  Pass chaining follows WaveletNoise.cpp:153-182 (3D) and :87-107 (2D).
+static int tile_build_device(wn_tile *t, const float *dR)
+{
+    wn_ctx *c = t->ctx;
+    cudaStream_t st = c->stream;
+    const size_t bytes = t->count * sizeof(float);
+    float *t1 = nullptr, *t2 = nullptr;
+    WN_CUDA(cudaMallocAsync(&t1, bytes, st));
+    WN_CUDA(cudaMallocAsync(&t2, bytes, st));
+    int nl = 0, r;
+    const bool odd = (t->flags & WN_TILE_ODD_OFFSET) != 0;
+    if (t->dims == 3) {
+        if ((r = wn_launch_filter_axis(dR, t1, nullptr, t->n, 3, 0, st)) < 0) goto bad; nl += r;
+        if ((r = wn_launch_filter_axis(t1, t2, nullptr, t->n, 3, 1, st)) < 0) goto bad; nl += r;
+        // z pass writes N = R - (...) directly; with the odd-offset flag it goes through t1 -> t->d
+        if (odd) {
+            if ((r = wn_launch_filter_axis(t2, t1, dR, t->n, 3, 2, st)) < 0) goto bad; nl += r;
+            nl += wn_launch_odd_offset3d(t1, t->d, t->n, st);
+        } else {
+            if ((r = wn_launch_filter_axis(t2, t->d, dR, t->n, 3, 2, st)) < 0) goto bad; nl += r;
+        }
+    } else {
+        if ((r = wn_launch_filter_axis(dR, t1, nullptr, t->n, 2, 0, st)) < 0) goto bad; nl += r;
+        if ((r = wn_launch_filter_axis(t1, t->d, dR, t->n, 2, 1, st)) < 0) goto bad; nl += r;
+    }
+    c->launches += (uint64_t)nl;
+    WN_CUDA(cudaGetLastError());
+    WN_CUDA(cudaFreeAsync(t1, st));
+    WN_CUDA(cudaFreeAsync(t2, st));
+    t->built = true;
+    return WN_OK;
+bad:
+    cudaFreeAsync(t1, st); cudaFreeAsync(t2, st);
+    return wn_fail(WN_EINVAL, "tile size %d does not fit the filter kernels' shared memory", t->n);
+}
+
+extern "C" int wn_tile_build_from_gaussian(wn_tile *t, const float *R, int space)
+{
+    WN_REQUIRE(t && R, "wn_tile_build_from_gaussian: NULL argument");
+    wn_ctx *c = t->ctx;
+    DeviceGuard g(c->device);
+    if (space == WN_DEVICE) return tile_build_device(t, R);
+    WN_REQUIRE(space == WN_HOST, "bad space %d", space);
+    float *dR = nullptr;
+    const size_t bytes = t->count * sizeof(float);
+    WN_CUDA(cudaMallocAsync(&dR, bytes, c->stream));
+    WN_CUDA(cudaMemcpyAsync(dR, R, bytes, cudaMemcpyHostToDevice, c->stream));
+    timing_begin(c);
+    timing_mark(c, c->stream);
+    int r = tile_build_device(t, dR);
+    timing_mark(c, c->stream);
+    cudaFreeAsync(dR, c->stream);
+    if (r) return r;
+    WN_CUDA(cudaStreamSynchronize(c->stream));
+    return timing_end(c);
+}
+
+extern "C" int wn_tile_build_seeded(wn_tile *t, unsigned seed)
+{
+    WN_REQUIRE(t, "wn_tile_build_seeded: tile is NULL");
+    // round-1 slice: the Gaussian field comes from the reference's own host generator objects
+    // (std::mt19937 + std::normal_distribution<float>), then H2D + device filter passes.
+    std::vector<float> R(t->count);
+    wn_rng rng(seed);
+    for (size_t i = 0; i < t->count; ++i) R[i] = rng.gauss(rng.engine);
+    return wn_tile_build_from_gaussian(t, R.data(), WN_HOST);
+}
+
+extern "C" int wn_tile_upload(wn_tile *t, const float *N, int space)
+{
+    WN_REQUIRE(t && N, "wn_tile_upload: NULL argument");
+    DeviceGuard g(t->ctx->device);
+    WN_CUDA(cudaMemcpyAsync(t->d, N, t->count * sizeof(float),
+                            space == WN_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, t->ctx->stream));
+    if (space != WN_DEVICE) WN_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    t->built = true;
+    return WN_OK;
+}
+
+extern "C" int wn_tile_download(const wn_tile *t, float *out, int space)
+{
+    WN_REQUIRE(t && out, "wn_tile_download: NULL argument");
+    if (!t->built) return wn_fail(WN_ESTATE, "wn_tile_download: the tile has not been built");
+    DeviceGuard g(t->ctx->device);
+    WN_CUDA(cudaMemcpyAsync(out, t->d, t->count * sizeof(float),
+                            space == WN_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, t->ctx->stream));
+    if (space != WN_DEVICE) WN_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    return WN_OK;
+}
+
+extern "C" int wn_tile_device_ptr(const wn_tile *t, void **dptr)
+{
+    WN_REQUIRE(t && dptr, "wn_tile_device_ptr: NULL argument");
+    *dptr = t->d;
+    return WN_OK;
+}
+
+extern "C" int wn_tile_mark_built(wn_tile *t)
+{
+    WN_REQUIRE(t, "wn_tile_mark_built: tile is NULL");
+    t->built = true;
+    return WN_OK;
+}
+
+#define WN_NEED_TILE(t, d, who)                                                                    \
+    do {                                                                                           \
+        WN_REQUIRE((t), who ": tile is NULL");                                                     \
+        WN_REQUIRE((t)->dims == (d), who ": needs a %dD tile (this one is %dD)", (d), (t)->dims);  \
+        if (!(t)->built) return wn_fail(WN_ESTATE, who ": the tile has not been built");           \
+    } while (0)
+
+#define WN_NEED_SPACE(space) WN_REQUIRE((space) == WN_HOST || (space) == WN_DEVICE, "bad space %d", (space))
+
+static int make_bands(const float *scale, const float *weights, int nbands, float post, WnBands *b)
+{
+    WN_REQUIRE(nbands >= 1 && nbands <= WN_MAX_BANDS, "nbands must be in [1,%d] (got %d)", WN_MAX_BANDS, nbands);
+    WN_REQUIRE(scale && weights, "band_scale / weights is NULL");
+    b->nbands = nbands;
+    for (int i = 0; i < WN_MAX_BANDS; ++i) { b->scale[i] = i < nbands ? scale[i] : 0.0f; b->weight[i] = i < nbands ? weights[i] : 0.0f; }
+    b->post = post;
+    return WN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// points
+// ---------------------------------------------------------------------------------------------------
+extern "C" int wn_eval2d_points(const wn_tile *t, const float *p, size_t count, float pre, float post, float *out, int space)
+{
+    WN_NEED_TILE(t, 2, "wn_eval2d_points");
+    WN_NEED_SPACE(space);
+    if (!count) return WN_OK;
+    WN_REQUIRE(p && out, "wn_eval2d_points: NULL buffer");
+    wn_ctx *c = t->ctx;
+    DeviceGuard g(c->device);
+    const WnTileView tv = tile_view(t);
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_eval2d_points(tv, WnPointsAoS{p, pre}, 0, count, post, out, st); });
+    ChunkIO io; io.in = p; io.in_item = 2 * sizeof(float); io.out = out;
+    return run_chunked_host(c, count, kChunkSamples, io, [&](void *din, void *, float *dout, size_t, size_t cnt, cudaStream_t st) {
+        return wn_launch_eval2d_points(tv, WnPointsAoS{(const float *)din, pre}, 0, cnt, post, dout, st);
+    });
+}
+
+extern "C" int wn_multiband3d_points(const wn_tile *t, const float *p, size_t count, const float *band_scale,
+                                     const float *weights, int nbands, float post, float *out, int space)
+{
+    WN_NEED_TILE(t, 3, "wn_multiband3d_points");
+    WN_NEED_SPACE(space);
+    WnBands b;
+    int r = make_bands(band_scale, weights, nbands, post, &b);
+    if (r) return r;
+    if (!count) return WN_OK;
+    WN_REQUIRE(p && out, "wn_multiband3d_points: NULL buffer");
+    wn_ctx *c = t->ctx;
+    DeviceGuard g(c->device);
+    const WnTileView tv = tile_view(t);
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_mb3d_points(tv, WnPointsAoS{p, 1.0f}, b, 0, count, out, st); });
+    ChunkIO io; io.in = p; io.in_item = 3 * sizeof(float); io.out = out;
+    return run_chunked_host(c, count, kChunkSamples, io, [&](void *din, void *, float *dout, size_t, size_t cnt, cudaStream_t st) {
+        return wn_launch_mb3d_points(tv, WnPointsAoS{(const float *)din, 1.0f}, b, 0, cnt, dout, st);
+    });
+}
+
+// evaluate3D(p*pre)*post == multiband with one band {scale=pre, weight=1}: 0 + 1*v == v and v*post, bit-exact
+extern "C" int wn_eval3d_points(const wn_tile *t, const float *p, size_t count, float pre, float post, float *out, int space)
+{
+    const float one = 1.0f;
+    return wn_multiband3d_points(t, p, count, &pre, &one, 1, post, out, space);
+}
+
+extern "C" int wn_eval3d_projected_points(const wn_tile *t, const float *p, const float *normals, int shared,
+                                          size_t count, float pre, float post, float *out, int space)
+{
+    WN_NEED_TILE(t, 3, "wn_eval3d_projected_points");
+    WN_NEED_SPACE(space);
+    if (!count) return WN_OK;
+    WN_REQUIRE(p && out && normals, "wn_eval3d_projected_points: NULL buffer");
+    wn_ctx *c = t->ctx;
+    DeviceGuard g(c->device);
+    const WnTileView tv = tile_view(t);
+    float nrm[3] = { 0, 0, 0 };
+    if (shared) { nrm[0] = normals[0]; nrm[1] = normals[1]; nrm[2] = normals[2]; }
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) {
+            return wn_launch_proj_points(tv, WnPointsAoS{p, pre}, shared ? nullptr : normals, nrm, 0, count, post, out, st);
+        });
+    ChunkIO io; io.in = p; io.in_item = 3 * sizeof(float); io.out = out;
+    if (!shared) { io.aux = normals; io.aux_item = 3 * sizeof(float); }
+    return run_chunked_host(c, count, kChunkSamples / 4, io, [&](void *din, void *daux, float *dout, size_t, size_t cnt, cudaStream_t st) {
+        return wn_launch_proj_points(tv, WnPointsAoS{(const float *)din, pre}, shared ? nullptr : (const float *)daux, nrm,
+                                     0, cnt, post, dout, st);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------
+// lattices and affine grids
+// ---------------------------------------------------------------------------------------------------
+static int check_axes(const float *xs, int nx, const float *ys, int ny, const float *zs, int nz, bool need_z)
+{
+    WN_REQUIRE(nx >= 0 && ny >= 0 && nz >= 0, "negative lattice size");
+    WN_REQUIRE((xs || !nx) && (ys || !ny) && (!need_z || zs || !nz), "lattice axis pointer is NULL");
+    return WN_OK;
+}
+
+extern "C" int wn_eval2d_lattice(const wn_tile *t, const float *xs, int nx, const float *ys, int ny, float pre, float post,
+                                 float *out, int space)
+{
+    WN_NEED_TILE(t, 2, "wn_eval2d_lattice");
+    WN_NEED_SPACE(space);
+    int r = check_axes(xs, nx, ys, ny, nullptr, 1, false);
+    if (r) return r;
+    const size_t total = (size_t)nx * ny;
+    if (!total) return WN_OK;
+    WN_REQUIRE(out, "wn_eval2d_lattice: out is NULL");
+    wn_ctx *c = t->ctx;
+    DeviceGuard g(c->device);
+    ParamWriter pw(c);
+    if ((r = pw.reserve(((size_t)nx + ny) * sizeof(float) + 1024))) return r;
+    WnLattice L{nullptr, nullptr, nullptr, nx, ny, 1};
+    if ((r = pw.put(xs, nx * sizeof(float), (const void **)&L.xs))) return r;
+    if ((r = pw.put(ys, ny * sizeof(float), (const void **)&L.ys))) return r;
+    const WnTileView tv = tile_view(t);
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_eval2d_lattice(tv, L, pre, 0, total, post, out, st); });
+    ChunkIO io; io.out = out;
+    return run_chunked_host(c, total, kChunkSamples, io, [&](void *, void *, float *dout, size_t first, size_t cnt, cudaStream_t st) {
+        return wn_launch_eval2d_lattice(tv, L, pre, first, cnt, post, dout, st);
+    });
+}
+
+extern "C" int wn_multiband3d_lattice(const wn_tile *t, const float *xs, int nx, const float *ys, int ny, const float *zs,
+                                      int nz, const float *band_scale, const float *weights, int nbands, float post,
+                                      int mode, float *out, int space)
+{
+    WN_NEED_TILE(t, 3, "wn_multiband3d_lattice");
+    WN_NEED_SPACE(space);
+    WN_REQUIRE(mode == WN_EVAL_FAST || mode == WN_EVAL_EXACT, "bad mode %d", mode);
+    int r = check_axes(xs, nx, ys, ny, zs, nz, true);
+    if (r) return r;
+    WnBands b;
+    if ((r = make_bands(band_scale, weights, nbands, post, &b))) return r;
+    const size_t slice = (size_t)nx * ny, total = slice * nz;
+    if (!total) return WN_OK;
+    WN_REQUIRE(out, "wn_multiband3d_lattice: out is NULL");
+    wn_ctx *c = t->ctx;
+    DeviceGuard g(c->device);
+    ParamWriter pw(c);
+    if ((r = pw.reserve(((size_t)nx + ny + nz) * sizeof(float) + 2048))) return r;
+    WnLattice L{nullptr, nullptr, nullptr, nx, ny, nz};
+    if ((r = pw.put(xs, nx * sizeof(float), (const void **)&L.xs))) return r;
+    if ((r = pw.put(ys, ny * sizeof(float), (const void **)&L.ys))) return r;
+    if ((r = pw.put(zs, nz * sizeof(float), (const void **)&L.zs))) return r;
+    const WnTileView tv = tile_view(t);
+    if (mode == WN_EVAL_EXACT) {
+        if (space == WN_DEVICE)
+            return run_device(c, [&](cudaStream_t st) { return wn_launch_mb3d_lattice_exact(tv, L, b, 0, total, out, st); });
+        ChunkIO io; io.out = out;
+        return run_chunked_host(c, total, kChunkSamples, io, [&](void *, void *, float *dout, size_t first, size_t cnt, cudaStream_t st) {
+            return wn_launch_mb3d_lattice_exact(tv, L, b, first, cnt, dout, st);
+        });
+    }
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_mb3d_lattice_fast(tv, L, b, 0, nz, out, st); });
+    // HOST: chunk by whole z slices so each chunk is a lattice slab
+    size_t slices_per_chunk = std::max<size_t>(1, kChunkSamples / slice);
+    ChunkIO io; io.out = out; io.out_item = slice * sizeof(float);
+    return run_chunked_host(c, (size_t)nz, slices_per_chunk, io, [&](void *, void *, float *dout, size_t first, size_t cnt, cudaStream_t st) {
+        return wn_launch_mb3d_lattice_fast(tv, L, b, (int)first, (int)cnt, dout, st);
+    });
+}
+
+static int make_affine(ParamWriter &pw, const float origin[3], const float e1[3], const float *us, int nu,
+                       const float e2[3], const float *vs, int nv, float pre, WnAffine *A)
+{
+    WN_REQUIRE(origin && e1 && e2, "affine grid: origin/e1/e2 is NULL");
+    WN_REQUIRE(nu >= 0 && nv >= 0 && (us || !nu) && (vs || !nv), "affine grid: bad axes");
+    int r;
+    if ((r = pw.reserve(((size_t)nu + nv) * sizeof(float) + 1024))) return r;
+    A->nu = nu; A->nv = nv; A->pre = pre;
+    for (int i = 0; i < 3; ++i) { A->o[i] = origin[i]; A->e1[i] = e1[i]; A->e2[i] = e2[i]; }
+    if ((r = pw.put(us, nu * sizeof(float), (const void **)&A->us))) return r;
+    if ((r = pw.put(vs, nv * sizeof(float), (const void **)&A->vs))) return r;
+    return WN_OK;
+}
+
+extern "C" int wn_eval3d_projected_grid(const wn_tile *t, const float origin[3], const float e1[3], const float *us, int nu,
+                                        const float e2[3], const float *vs, int nv, const float normal[3], float pre,
+                                        float post, float *out, int space)
+{
+    WN_NEED_TILE(t, 3, "wn_eval3d_projected_grid");
+    WN_NEED_SPACE(space);
+    WN_REQUIRE(normal, "wn_eval3d_projected_grid: normal is NULL");
+    wn_ctx *c = t->ctx;
+    DeviceGuard g(c->device);
+    ParamWriter pw(c);
+    WnAffine A;
+    int r = make_affine(pw, origin, e1, us, nu, e2, vs, nv, pre, &A);
+    if (r) return r;
+    const size_t total = (size_t)nu * nv;
+    if (!total) return WN_OK;
+    WN_REQUIRE(out, "wn_eval3d_projected_grid: out is NULL");
+    const WnTileView tv = tile_view(t);
+    const float nrm[3] = { normal[0], normal[1], normal[2] };
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_proj_affine(tv, A, nrm, 0, total, post, out, st); });
+    ChunkIO io; io.out = out;
+    return run_chunked_host(c, total, kChunkSamples / 4, io, [&](void *, void *, float *dout, size_t first, size_t cnt, cudaStream_t st) {
+        return wn_launch_proj_affine(tv, A, nrm, first, cnt, post, dout, st);
+    });
+}
+
+extern "C" int wn_eval3d_grid(const wn_tile *t, const float origin[3], const float e1[3], const float *us, int nu,
+                              const float e2[3], const float *vs, int nv, float pre, float post, float *out, int space)
+{
+    WN_NEED_TILE(t, 3, "wn_eval3d_grid");
+    WN_NEED_SPACE(space);
+    wn_ctx *c = t->ctx;
+    DeviceGuard g(c->device);
+    ParamWriter pw(c);
+    WnAffine A;
+    int r = make_affine(pw, origin, e1, us, nu, e2, vs, nv, pre, &A);
+    if (r) return r;
+    const size_t total = (size_t)nu * nv;
+    if (!total) return WN_OK;
+    WN_REQUIRE(out, "wn_eval3d_grid: out is NULL");
+    const WnTileView tv = tile_view(t);
+    WnBands b;
+    const float one = 1.0f;
+    make_bands(&one, &one, 1, post, &b);        // the pre-scale is applied by the affine generator
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_mb3d_affine(tv, A, b, 0, total, out, st); });
+    ChunkIO io; io.out = out;
+    return run_chunked_host(c, total, kChunkSamples, io, [&](void *, void *, float *dout, size_t first, size_t cnt, cudaStream_t st) {
+        return wn_launch_mb3d_affine(tv, A, b, first, cnt, dout, st);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Perlin
+// ---------------------------------------------------------------------------------------------------
+struct wn_perlin {
+    wn_ctx *ctx = nullptr;
+    int32_t *d = nullptr;
+};
+
+extern "C" int wn_perlin_create(wn_ctx *c, const int32_t perm[512], wn_perlin **out)
+{
+    WN_REQUIRE(c && perm && out, "wn_perlin_create: NULL argument");
+    *out = nullptr;
+    for (int i = 0; i < 512; ++i)
+        WN_REQUIRE(perm[i] >= 0 && perm[i] < 256, "wn_perlin_create: perm[%d]=%d outside [0,255]", i, perm[i]);
+    DeviceGuard g(c->device);
+    wn_perlin *p = new (std::nothrow) wn_perlin();
+    if (!p) return wn_fail(WN_ENOMEM, "out of host memory");
+    p->ctx = c;
+    if (cudaMalloc(&p->d, 512 * sizeof(int32_t)) != cudaSuccess) { delete p; cudaGetLastError(); return wn_fail(WN_ENOMEM, "cudaMalloc failed"); }
+    WN_CUDA(cudaMemcpyAsync(p->d, perm, 512 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    WN_CUDA(cudaStreamSynchronize(c->stream));
+    *out = p;
+    return WN_OK;
+}
+
+extern "C" int wn_perlin_destroy(wn_perlin *p)
+{
+    if (!p) return WN_OK;
+    DeviceGuard g(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    cudaFree(p->d);
+    delete p;
+    return WN_OK;
+}
+
+extern "C" int wn_perlin_points(const wn_perlin *pn, const float *p, size_t count, float pre, float *out, int space)
+{
+    WN_REQUIRE(pn, "wn_perlin_points: perlin is NULL");
+    WN_NEED_SPACE(space);
+    if (!count) return WN_OK;
+    WN_REQUIRE(p && out, "wn_perlin_points: NULL buffer");
+    wn_ctx *c = pn->ctx;
+    DeviceGuard g(c->device);
+    const int32_t *perm = pn->d;
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_perlin_points(perm, WnPointsAoS{p, pre}, 0, count, out, st); });
+    ChunkIO io; io.in = p; io.in_item = 3 * sizeof(float); io.out = out;
+    return run_chunked_host(c, count, kChunkSamples, io, [&](void *din, void *, float *dout, size_t, size_t cnt, cudaStream_t st) {
+        return wn_launch_perlin_points(perm, WnPointsAoS{(const float *)din, pre}, 0, cnt, dout, st);
+    });
+}
+
+extern "C" int wn_perlin_lattice(const wn_perlin *pn, const float *xs, int nx, const float *ys, int ny, const float *zs, int nz,
+                                 float *out, int space)
+{
+    WN_REQUIRE(pn, "wn_perlin_lattice: perlin is NULL");
+    WN_NEED_SPACE(space);
+    int r = check_axes(xs, nx, ys, ny, zs, nz, true);
+    if (r) return r;
+    const size_t total = (size_t)nx * ny * nz;
+    if (!total) return WN_OK;
+    WN_REQUIRE(out, "wn_perlin_lattice: out is NULL");
+    wn_ctx *c = pn->ctx;
+    DeviceGuard g(c->device);
+    ParamWriter pw(c);
+    if ((r = pw.reserve(((size_t)nx + ny + nz) * sizeof(float) + 2048))) return r;
+    WnLattice L{nullptr, nullptr, nullptr, nx, ny, nz};
+    if ((r = pw.put(xs, nx * sizeof(float), (const void **)&L.xs))) return r;
+    if ((r = pw.put(ys, ny * sizeof(float), (const void **)&L.ys))) return r;
+    if ((r = pw.put(zs, nz * sizeof(float), (const void **)&L.zs))) return r;
+    const int32_t *perm = pn->d;
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_perlin_lattice(perm, L, 0, total, out, st); });
+    ChunkIO io; io.out = out;
+    return run_chunked_host(c, total, kChunkSamples, io, [&](void *, void *, float *dout, size_t first, size_t cnt, cudaStream_t st) {
+        return wn_launch_perlin_lattice(perm, L, first, cnt, dout, st);
+    });
+}
+
+extern "C" int wn_perlin_grid(const wn_perlin *pn, const float origin[3], const float e1[3], const float *us, int nu,
+                              const float e2[3], const float *vs, int nv, float pre, float *out, int space)
+{
+    WN_REQUIRE(pn, "wn_perlin_grid: perlin is NULL");
+    WN_NEED_SPACE(space);
+    wn_ctx *c = pn->ctx;
+    DeviceGuard g(c->device);
+    ParamWriter pw(c);
+    WnAffine A;
+    int r = make_affine(pw, origin, e1, us, nu, e2, vs, nv, pre, &A);
+    if (r) return r;
+    const size_t total = (size_t)nu * nv;
+    if (!total) return WN_OK;
+    WN_REQUIRE(out, "wn_perlin_grid: out is NULL");
+    const int32_t *perm = pn->d;
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_perlin_affine(perm, A, 0, total, out, st); });
+    ChunkIO io; io.out = out;
+    return run_chunked_host(c, total, kChunkSamples, io, [&](void *, void *, float *dout, size_t first, size_t cnt, cudaStream_t st) {
+        return wn_launch_perlin_affine(perm, A, first, cnt, dout, st);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------
+// texture hooks
+// ---------------------------------------------------------------------------------------------------
+extern "C" int wn_wavelet_texture_values(const wn_tile *t, const float *p, size_t count, double scale, int octave,
+                                         float *grey, int space)
+{
+    WN_NEED_TILE(t, 3, "wn_wavelet_texture_values");
+    WN_NEED_SPACE(space);
+    if (!count) return WN_OK;
+    WN_REQUIRE(p && grey, "wn_wavelet_texture_values: NULL buffer");
+    wn_ctx *c = t->ctx;
+    DeviceGuard g(c->device);
+    // texture.h:77-80,84: octave_scale = std::pow(2.0f, octave) narrowed to float; pos *= octave_scale*2.0f
+    const float octave_scale = (float)std::pow(2.0, (double)octave);
+    const float oct2 = octave_scale * 2.0f;
+    const float inv_std = 1.0f / std::sqrt(0.18402f);
+    const WnTileView tv = tile_view(t);
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_wavelet_texture(tv, p, count, scale, oct2, inv_std, grey, st); });
+    ChunkIO io; io.in = p; io.in_item = 3 * sizeof(float); io.out = grey;
+    return run_chunked_host(c, count, kChunkSamples, io, [&](void *din, void *, float *dout, size_t, size_t cnt, cudaStream_t st) {
+        return wn_launch_wavelet_texture(tv, (const float *)din, cnt, scale, oct2, inv_std, dout, st);
+    });
+}
+
+extern "C" int wn_perlin_texture_values(const wn_perlin *pn, const float *p, size_t count, double scale, int octave,
+                                        float *grey, int space)
+{
+    WN_REQUIRE(pn, "wn_perlin_texture_values: perlin is NULL");
+    WN_NEED_SPACE(space);
+    if (!count) return WN_OK;
+    WN_REQUIRE(p && grey, "wn_perlin_texture_values: NULL buffer");
+    wn_ctx *c = pn->ctx;
+    DeviceGuard g(c->device);
+    const float octave_scale = (float)std::pow(2.0, (double)octave);
+    const float scale_f = (float)scale;                      // vec3 * double -> operator*(vec3, float)
+    const int32_t *perm = pn->d;
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_perlin_texture(perm, p, count, scale_f, octave_scale, grey, st); });
+    ChunkIO io; io.in = p; io.in_item = 3 * sizeof(float); io.out = grey;
+    return run_chunked_host(c, count, kChunkSamples, io, [&](void *din, void *, float *dout, size_t, size_t cnt, cudaStream_t st) {
+        return wn_launch_perlin_texture(perm, (const float *)din, cnt, scale_f, octave_scale, dout, st);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stats
+// ---------------------------------------------------------------------------------------------------
+extern "C" int wn_stats_compute(wn_ctx *c, const float *data, size_t count, int space, wn_stats *out)
+{
+    WN_REQUIRE(c && out, "wn_stats_compute: NULL argument");
+    WN_NEED_SPACE(space);
+    wn_stats s;
+    s.avg = 0.0f; s.var = 0.0f;
+    s.min_val = 3.402823466e+38f; s.max_val = -3.402823466e+38f;      // DataStats defaults, WaveletNoise.h:12-17
+    s.count_nan_inf = 0; s.energy = 0.0f;
+    *out = s;
+    if (!count) return WN_OK;
+    WN_REQUIRE(data, "wn_stats_compute: data is NULL");
+    DeviceGuard g(c->device);
+    int r = buf_reserve(c->stats_partial, 4 * WN_STATS_BLOCKS * sizeof(double));
+    if (r) return r;
+    const float *dd = data;
+    if (space == WN_HOST) {
+        if ((r = buf_reserve(c->in[0], count * sizeof(float)))) return r;
+        WN_CUDA(cudaMemcpyAsync(c->in[0].p, data, count * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        dd = (const float *)c->in[0].p;
+    }
+    c->launches += (uint64_t)wn_launch_stats(dd, count, (double *)c->stats_partial.p, c->stream);
+    WN_CUDA(cudaGetLastError());
+    std::vector<double> part(4 * WN_STATS_BLOCKS);
+    WN_CUDA(cudaMemcpyAsync(part.data(), c->stats_partial.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    WN_CUDA(cudaStreamSynchronize(c->stream));
+    double sum = 0.0, sq = 0.0;
+    for (int b = 0; b < WN_STATS_BLOCKS; ++b) {
+        sum += part[4 * b]; sq += part[4 * b + 1];
+        s.min_val = std::min(s.min_val, (float)part[4 * b + 2]);
+        s.max_val = std::max(s.max_val, (float)part[4 * b + 3]);
+    }
+    s.avg = (float)(sum / (double)count);
+    s.var = (float)((sq / (double)count) - (double)s.avg * s.avg);
+    *out = s;
+    return WN_OK;
+}

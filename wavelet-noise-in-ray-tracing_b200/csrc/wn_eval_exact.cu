@@ -1,0 +1,403 @@
+// wn_eval_exact.cu -- reference-order evaluators (kernels K5..K10 of DESIGN.md), one sample per thread.
+//
+// Everything here reproduces the reference's floating-point operation ORDER and WIDTH with explicit
+// round-to-nearest intrinsics (__fmul_rn / __fadd_rn / __dmul_rn ...), which nvcc never contracts into
+// FMAs; the file is additionally built with -fmad=false.  ceilf/floorf/sqrtf/fabsf and float<->int
+// conversions are exact IEEE operations on both sides, so for in-range inputs the results are
+// BIT-IDENTICAL to the CPU reference (checked against the 15 shipped .raw images).
+//
+//   evaluate2D            WaveletNoise.cpp:111-140      eval2d()
+//   evaluate3D            WaveletNoise.cpp:185-215      eval3d()
+//   evaluate3DProjected   WaveletNoise.cpp:218-265      eval3d_projected()
+//   PerlinNoise::noise    experient/PerlinNoise.hpp:13-56 (== perlin.h:17-62)   perlin3()
+//   wavelet_texture/noise_texture::value   texture.h:67-107 / :37-43
+//   calculateStats        WaveletNoise.cpp:268-288
+//
+// The tile (8 MiB at n = 128) stays L2-resident; taps are read through the read-only path.
+#include "wn_internal.h"
+
+namespace {
+
+#define FMUL __fmul_rn
+#define FADD __fadd_rn
+#define FSUB __fsub_rn
+
+__device__ __forceinline__ int tmod(int x, const WnTileView &t)          // Mod(), cpp:31-34
+{
+    if (t.pow2) return x & (t.n - 1);
+    int m = x % t.n;
+    return m < 0 ? m + t.n : m;
+}
+
+// quadratic B-spline weights of one axis (cpp:121-127 / :194-200)
+__device__ __forceinline__ void basis(float p, int &mid, float w[3])
+{
+    const float a = FSUB(p, 0.5f);
+    mid = (int)ceilf(a);
+    const float t = FSUB((float)mid, a);
+    w[0] = FMUL(FMUL(t, t), 0.5f);                       // t*t/2.0f  (x/2 == x*0.5 exactly)
+    const float s = FSUB(1.0f, t);
+    w[2] = FMUL(FMUL(s, s), 0.5f);
+    w[1] = FSUB(FSUB(1.0f, w[0]), w[2]);
+}
+
+__device__ __forceinline__ float eval2d(const WnTileView &t, float px, float py)
+{
+    int mx, my; float wx[3], wy[3];
+    basis(px, mx, wx); basis(py, my, wy);
+    int cx[3], cy[3];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) { cx[f] = tmod(mx + f - 1, t); cy[f] = tmod(my + f - 1, t) * t.n; }
+    float r = 0.0f;
+#pragma unroll
+    for (int fy = 0; fy < 3; ++fy)
+#pragma unroll
+        for (int fx = 0; fx < 3; ++fx)
+            r = FADD(r, FMUL(FMUL(wx[fx], wy[fy]), __ldg(t.N + cx[fx] + cy[fy])));
+    return r;
+}
+
+__device__ __forceinline__ float eval3d(const WnTileView &t, float px, float py, float pz)
+{
+    int mx, my, mz; float wx[3], wy[3], wz[3];
+    basis(px, mx, wx); basis(py, my, wy); basis(pz, mz, wz);
+    int cx[3], cy[3], cz[3];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+        cx[f] = tmod(mx + f - 1, t);
+        cy[f] = tmod(my + f - 1, t) * t.n;
+        cz[f] = tmod(mz + f - 1, t) * t.n * t.n;
+    }
+    float r = 0.0f;
+#pragma unroll
+    for (int fz = 0; fz < 3; ++fz)
+#pragma unroll
+        for (int fy = 0; fy < 3; ++fy)
+#pragma unroll
+            for (int fx = 0; fx < 3; ++fx)          // weight = (wx*wy)*wz, cpp:206
+                r = FADD(r, FMUL(FMUL(FMUL(wx[fx], wy[fy]), wz[fz]), __ldg(t.N + cx[fx] + cy[fy] + cz[fz])));
+    return r;
+}
+
+__device__ __forceinline__ float multiband3d(const WnTileView &t, const WnBands &b, float x, float y, float z)
+{
+    float acc = 0.0f;
+    for (int k = 0; k < b.nbands; ++k) {
+        const float s = b.scale[k];
+        acc = FADD(acc, FMUL(b.weight[k], eval3d(t, FMUL(x, s), FMUL(y, s), FMUL(z, s))));
+    }
+    return FMUL(acc, b.post);
+}
+
+__device__ float eval3d_projected(const WnTileView &t, const float p[3], const float nrm[3])
+{
+    int lo[3], hi[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        // support = 3|n_i| + 3 sqrt((1 - n_i^2)/2), cpp:229
+        const float support = FADD(FMUL(3.0f, fabsf(nrm[i])),
+                                   FMUL(3.0f, __fsqrt_rn(FMUL(FSUB(1.0f, FMUL(nrm[i], nrm[i])), 0.5f))));
+        lo[i] = (int)ceilf(FSUB(p[i], support));
+        hi[i] = (int)floorf(FADD(p[i], support));
+    }
+    // |support| <= 3 + 3/sqrt(2) for a unit normal, so a box wider than 12 cells means non-finite or
+    // out-of-int-range input (undefined behaviour in the reference); refuse instead of looping forever.
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        if (hi[i] - lo[i] > 12 || hi[i] < lo[i] - 1 || hi[i] == 0x7fffffff) return 0.0f;
+    const float q0 = FSUB(p[0], 1.5f), q1 = FSUB(p[1], 1.5f), q2 = FSUB(p[2], 1.5f);
+    float result = 0.0f;
+    for (int c2 = lo[2]; c2 <= hi[2]; ++c2) {
+        const float f2 = (float)c2;
+        const int i2 = tmod(c2, t) * t.n * t.n;
+        for (int c1 = lo[1]; c1 <= hi[1]; ++c1) {
+            const float f1 = (float)c1;
+            const int i1 = tmod(c1, t) * t.n;
+            for (int c0 = lo[0]; c0 <= hi[0]; ++c0) {
+                const float f0 = (float)c0;
+                // dot = ((0 + n0 (p0-c0)) + n1 (p1-c1)) + n2 (p2-c2), cpp:239-240
+                float dot = FADD(0.0f, FMUL(nrm[0], FSUB(p[0], f0)));
+                dot = FADD(dot, FMUL(nrm[1], FSUB(p[1], f1)));
+                dot = FADD(dot, FMUL(nrm[2], FSUB(p[2], f2)));
+                float weight = 1.0f;
+                const float fc[3] = { f0, f1, f2 };
+                const float qq[3] = { q0, q1, q2 };
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    // t = (c_i + n_i*dot/2) - (p_i - 1.5), cpp:245
+                    const float tt = FSUB(FADD(fc[i], FMUL(FMUL(nrm[i], dot), 0.5f)), qq[i]);
+                    if (tt <= 0.0f || tt >= 3.0f) { weight = 0.0f; break; }
+                    float piece;
+                    if (tt < 1.0f) piece = FMUL(FMUL(tt, tt), 0.5f);
+                    else if (tt < 2.0f) {
+                        const float t1 = FSUB(tt, 1.0f), t2 = FSUB(2.0f, tt);
+                        piece = FSUB(1.0f, FMUL(FADD(FMUL(t1, t1), FMUL(t2, t2)), 0.5f));
+                    } else {
+                        const float t3 = FSUB(3.0f, tt);
+                        piece = FMUL(FMUL(t3, t3), 0.5f);
+                    }
+                    weight = FMUL(weight, piece);
+                }
+                if ((double)weight > 1e-6)                     // float vs double literal, cpp:257
+                    result = FADD(result, FMUL(weight, __ldg(t.N + tmod(c0, t) + i1 + i2)));
+            }
+        }
+    }
+    return result;
+}
+
+// ---- Perlin, double precision -------------------------------------------------------------------
+__device__ __forceinline__ double pfade(double t)    // t*t*t*(t*(t*6-15)+10)
+{
+    const double inner = __dadd_rn(__dmul_rn(t, __dsub_rn(__dmul_rn(t, 6.0), 15.0)), 10.0);
+    return __dmul_rn(__dmul_rn(__dmul_rn(t, t), t), inner);
+}
+__device__ __forceinline__ double plerp(double t, double a, double b) { return __dadd_rn(a, __dmul_rn(t, __dsub_rn(b, a))); }
+__device__ __forceinline__ double pgrad(int hash, double x, double y, double z)
+{
+    const int h = hash & 15;
+    const double u = h < 8 ? x : y;
+    const double v = h < 4 ? y : ((h == 12 || h == 14) ? x : z);
+    return __dadd_rn((h & 1) == 0 ? u : -u, (h & 2) == 0 ? v : -v);
+}
+__device__ double perlin3(const int *p /* 512 ints, shared memory */, double x, double y, double z)
+{
+    const double fx = floor(x), fy = floor(y), fz = floor(z);
+    const int X = (int)fx & 255, Y = (int)fy & 255, Z = (int)fz & 255;
+    x = __dsub_rn(x, fx); y = __dsub_rn(y, fy); z = __dsub_rn(z, fz);
+    const double u = pfade(x), v = pfade(y), w = pfade(z);
+    const int A = p[X] + Y, AA = p[A] + Z, AB = p[A + 1] + Z;
+    const int B = p[X + 1] + Y, BA = p[B] + Z, BB = p[B + 1] + Z;
+    const double x1 = __dsub_rn(x, 1.0), y1 = __dsub_rn(y, 1.0), z1 = __dsub_rn(z, 1.0);
+    return plerp(w,
+        plerp(v, plerp(u, pgrad(p[AA], x, y, z),      pgrad(p[BA], x1, y, z)),
+                 plerp(u, pgrad(p[AB], x, y1, z),     pgrad(p[BB], x1, y1, z))),
+        plerp(v, plerp(u, pgrad(p[AA + 1], x, y, z1), pgrad(p[BA + 1], x1, y, z1)),
+                 plerp(u, pgrad(p[AB + 1], x, y1, z1), pgrad(p[BB + 1], x1, y1, z1))));
+}
+
+// ---- coordinate generators -------------------------------------------------------------------------
+__device__ __forceinline__ void coord2(const WnPointsAoS &c, size_t s, float p[3])
+{
+    p[0] = FMUL(__ldg(c.p + s * 2), c.pre);
+    p[1] = FMUL(__ldg(c.p + s * 2 + 1), c.pre);
+}
+__device__ __forceinline__ void coord(const WnPointsAoS &c, size_t s, float p[3])
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p[i] = FMUL(__ldg(c.p + s * 3 + i), c.pre);
+}
+__device__ __forceinline__ void coord(const WnLattice &c, size_t s, float p[3])
+{
+    const size_t row = s / c.nx;
+    p[0] = __ldg(c.xs + (s - row * c.nx));
+    const size_t k = row / c.ny;
+    p[1] = __ldg(c.ys + (row - k * c.ny));
+    p[2] = c.zs ? __ldg(c.zs + k) : 0.0f;
+}
+__device__ __forceinline__ void coord(const WnAffine &c, size_t s, float p[3])
+{
+    const size_t j = s / c.nu;
+    const float u = __ldg(c.us + (s - j * c.nu)), v = __ldg(c.vs + j);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        p[i] = FMUL(FADD(FADD(c.o[i], FMUL(u, c.e1[i])), FMUL(v, c.e2[i])), c.pre);
+}
+
+#define WN_TID_OR_RETURN(count)                                                        \
+    const size_t s = blockIdx.x * (size_t)blockDim.x + threadIdx.x;                    \
+    if (s >= (count)) return
+
+__global__ void k_eval2d_points(WnTileView t, WnPointsAoS c, size_t first, size_t count, float post, float *out)
+{
+    WN_TID_OR_RETURN(count);
+    float p[3]; coord2(c, first + s, p);
+    out[s] = FMUL(eval2d(t, p[0], p[1]), post);
+}
+__global__ void k_eval2d_lattice(WnTileView t, WnLattice c, float pre, size_t first, size_t count, float post, float *out)
+{
+    WN_TID_OR_RETURN(count);
+    float p[3]; coord(c, first + s, p);
+    out[s] = FMUL(eval2d(t, FMUL(p[0], pre), FMUL(p[1], pre)), post);
+}
+template <class C>
+__global__ void k_mb3d(WnTileView t, C c, WnBands b, size_t first, size_t count, float *out)
+{
+    WN_TID_OR_RETURN(count);
+    float p[3];
+    coord(c, first + s, p);
+    out[s] = multiband3d(t, b, p[0], p[1], p[2]);
+}
+template <class C>
+__global__ void k_proj(WnTileView t, C c, const float *normals, float n0, float n1, float n2, size_t first,
+                       size_t count, float post, float *out)
+{
+    WN_TID_OR_RETURN(count);
+    float p[3];
+    coord(c, first + s, p);
+    float nrm[3] = { n0, n1, n2 };
+    if (normals) { nrm[0] = __ldg(normals + 3 * s); nrm[1] = __ldg(normals + 3 * s + 1); nrm[2] = __ldg(normals + 3 * s + 2); }
+    out[s] = FMUL(eval3d_projected(t, p, nrm), post);
+}
+template <class C>
+__global__ void k_perlin(const int32_t *perm, C c, size_t first, size_t count, float *out)
+{
+    __shared__ int sp[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sp[i] = perm[i];
+    __syncthreads();
+    WN_TID_OR_RETURN(count);
+    float p[3];
+    coord(c, first + s, p);
+    out[s] = (float)perlin3(sp, (double)p[0], (double)p[1], (double)p[2]);
+}
+
+// texture.h:67-107 (3D branch).  oct2 = octave_scale * 2.0f (float), inv_std = 1.0f/sqrt(0.18402f)
+__global__ void k_wavelet_texture(WnTileView t, const float *p, size_t count, double scale, float oct2, float inv_std,
+                                  float *grey)
+{
+    WN_TID_OR_RETURN(count);
+    float q[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        q[i] = FMUL(__double2float_rn(__dmul_rn((double)__ldg(p + 3 * s + i), scale)), oct2);
+    double v = (double)eval3d(t, q[0], q[1], q[2]);
+    v = __dmul_rn(v, (double)inv_std);
+    double c = __ddiv_rn(v, 4.0);
+    c = (c < -1.0) ? -1.0 : ((1.0 < c) ? 1.0 : c);                 // std::clamp
+    grey[s] = __double2float_rn(__dmul_rn(0.5, __dadd_rn(1.0, c)));
+}
+// texture.h:37-43: (p * float(scale)) * octave_scale in float, Perlin in double, 0.5*(1+v)
+__global__ void k_perlin_texture(const int32_t *perm, const float *p, size_t count, float scale_f, float oct, float *grey)
+{
+    __shared__ int sp[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sp[i] = perm[i];
+    __syncthreads();
+    WN_TID_OR_RETURN(count);
+    double q[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) q[i] = (double)FMUL(FMUL(__ldg(p + 3 * s + i), scale_f), oct);
+    const double v = perlin3(sp, q[0], q[1], q[2]);
+    grey[s] = __double2float_rn(__dmul_rn(0.5, __dadd_rn(1.0, v)));
+}
+
+// calculateStats (cpp:268-288): double sums, float min/max.  Per-block partials, finished on the host.
+__global__ void k_stats(const float *__restrict__ data, size_t count, double *__restrict__ partial)
+{
+    double sum = 0.0, sq = 0.0;
+    float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = data[i];
+        sum += (double)v;
+        sq += (double)v * (double)v;
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    __shared__ double s_sum[8], s_sq[8];
+    __shared__ float s_mn[8], s_mx[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+        sq += __shfl_down_sync(0xffffffffu, sq, o);
+        mn = fminf(mn, __shfl_down_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_sum[warp] = sum; s_sq[warp] = sq; s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            sum += s_sum[w]; sq += s_sq[w]; mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]);
+        }
+        partial[4 * blockIdx.x + 0] = sum;
+        partial[4 * blockIdx.x + 1] = sq;
+        partial[4 * blockIdx.x + 2] = (double)mn;
+        partial[4 * blockIdx.x + 3] = (double)mx;
+    }
+}
+
+inline unsigned blocks_for(size_t count, int threads) { return (unsigned)((count + threads - 1) / threads); }
+
+} // namespace
+
+#define WN_T 256
+
+int wn_launch_eval2d_points(WnTileView t, WnPointsAoS c, size_t first, size_t count, float post, float *out, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_eval2d_points<<<blocks_for(count, WN_T), WN_T, 0, st>>>(t, c, first, count, post, out);
+    return 1;
+}
+int wn_launch_eval2d_lattice(WnTileView t, WnLattice c, float pre, size_t first, size_t count, float post, float *out, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_eval2d_lattice<<<blocks_for(count, WN_T), WN_T, 0, st>>>(t, c, pre, first, count, post, out);
+    return 1;
+}
+int wn_launch_mb3d_points(WnTileView t, WnPointsAoS c, WnBands b, size_t first, size_t count, float *out, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_mb3d<WnPointsAoS><<<blocks_for(count, WN_T), WN_T, 0, st>>>(t, c, b, first, count, out);
+    return 1;
+}
+int wn_launch_mb3d_lattice_exact(WnTileView t, WnLattice c, WnBands b, size_t first, size_t count, float *out, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_mb3d<WnLattice><<<blocks_for(count, WN_T), WN_T, 0, st>>>(t, c, b, first, count, out);
+    return 1;
+}
+int wn_launch_mb3d_affine(WnTileView t, WnAffine c, WnBands b, size_t first, size_t count, float *out, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_mb3d<WnAffine><<<blocks_for(count, WN_T), WN_T, 0, st>>>(t, c, b, first, count, out);
+    return 1;
+}
+int wn_launch_proj_points(WnTileView t, WnPointsAoS c, const float *normals, const float nrm[3], size_t first,
+                          size_t count, float post, float *out, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_proj<WnPointsAoS><<<blocks_for(count, 128), 128, 0, st>>>(t, c, normals, nrm[0], nrm[1], nrm[2], first, count, post, out);
+    return 1;
+}
+int wn_launch_proj_affine(WnTileView t, WnAffine c, const float nrm[3], size_t first, size_t count, float post,
+                          float *out, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_proj<WnAffine><<<blocks_for(count, 128), 128, 0, st>>>(t, c, nullptr, nrm[0], nrm[1], nrm[2], first, count, post, out);
+    return 1;
+}
+int wn_launch_perlin_points(const int32_t *perm, WnPointsAoS c, size_t first, size_t count, float *out, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_perlin<WnPointsAoS><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
+    return 1;
+}
+int wn_launch_perlin_lattice(const int32_t *perm, WnLattice c, size_t first, size_t count, float *out, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_perlin<WnLattice><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
+    return 1;
+}
+int wn_launch_perlin_affine(const int32_t *perm, WnAffine c, size_t first, size_t count, float *out, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_perlin<WnAffine><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
+    return 1;
+}
+int wn_launch_wavelet_texture(WnTileView t, const float *p, size_t count, double scale, float oct2, float inv_std,
+                              float *grey, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_wavelet_texture<<<blocks_for(count, WN_T), WN_T, 0, st>>>(t, p, count, scale, oct2, inv_std, grey);
+    return 1;
+}
+int wn_launch_perlin_texture(const int32_t *perm, const float *p, size_t count, float scale_f, float oct,
+                             float *grey, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_perlin_texture<<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, p, count, scale_f, oct, grey);
+    return 1;
+}
+int wn_launch_stats(const float *data, size_t count, double *partial, cudaStream_t st)
+{
+    k_stats<<<WN_STATS_BLOCKS, 256, 0, st>>>(data, count, partial);
+    return 1;
+}

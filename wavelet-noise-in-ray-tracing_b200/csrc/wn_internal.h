@@ -1,0 +1,80 @@
+// wn_internal.h -- declarations shared by the translation units of libwn_b200.so.
+// Kernels live in wn_tilegen.cu / wn_eval_exact.cu (compiled with -fmad=false: reference operation
+// order, un-fused IEEE arithmetic) and wn_multiband_fast.cu (FMA allowed).  wn_capi.cu is the only
+// file that implements the extern "C" surface of include/wn_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#define WN_MAX_BANDS 16
+
+// ---- sample-coordinate generators (device pointers) ---------------------------------------------
+// Every batch kernel is "for sample s in [first, first+count): out[s-first] = op(coord(s))".
+struct WnPointsAoS {            // scattered points, p*pre (one float multiply per component)
+    const float *p;             // xyz (or xy) per point
+    float pre;
+};
+struct WnLattice {              // axis-aligned: s = i + nx*(j + ny*k) -> (xs[i], ys[j], zs[k])
+    const float *xs, *ys, *zs;
+    int nx, ny, nz;
+};
+struct WnAffine {               // s = i + nu*j -> origin + us[i]*e1 + vs[j]*e2, then *pre
+    const float *us, *vs;
+    int nu, nv;
+    float o[3], e1[3], e2[3];
+    float pre;
+};
+
+struct WnBands {
+    int   nbands;
+    float scale[WN_MAX_BANDS];
+    float weight[WN_MAX_BANDS];
+    float post;
+};
+
+struct WnTileView {
+    const float *N;
+    int n;                      // tile edge
+    int pow2;                   // n is a power of two -> Mod is a mask
+};
+
+// ---- tile construction (wn_tilegen.cu) ------------------------------------------------------------
+// dst = filter_axis(src) for axis in {0,1,2}; when minuend != nullptr: dst = minuend - filter_axis(src).
+// tmp smem sizes are handled inside.  Returns the number of kernels launched.
+int wn_launch_filter_axis(const float *src, float *dst, const float *minuend, int n, int dims, int axis,
+                          cudaStream_t st);
+// paper odd-offset step: dst[x,y,z-transposed] = src + shifted src (see wn_tilegen.cu)
+int wn_launch_odd_offset3d(const float *src, float *dst, int n, cudaStream_t st);
+
+// ---- exact evaluators (wn_eval_exact.cu) ----------------------------------------------------------
+int wn_launch_eval2d_points(WnTileView t, WnPointsAoS c, size_t first, size_t count, float post, float *out, cudaStream_t st);
+int wn_launch_eval2d_lattice(WnTileView t, WnLattice c, float pre, size_t first, size_t count, float post, float *out, cudaStream_t st);
+int wn_launch_mb3d_points(WnTileView t, WnPointsAoS c, WnBands b, size_t first, size_t count, float *out, cudaStream_t st);
+int wn_launch_mb3d_lattice_exact(WnTileView t, WnLattice c, WnBands b, size_t first, size_t count, float *out, cudaStream_t st);
+int wn_launch_mb3d_affine(WnTileView t, WnAffine c, WnBands b, size_t first, size_t count, float *out, cudaStream_t st);
+// projected: normals == nullptr -> shared normal `nrm`
+int wn_launch_proj_points(WnTileView t, WnPointsAoS c, const float *normals, const float nrm[3], size_t first,
+                          size_t count, float post, float *out, cudaStream_t st);
+int wn_launch_proj_affine(WnTileView t, WnAffine c, const float nrm[3], size_t first, size_t count, float post,
+                          float *out, cudaStream_t st);
+int wn_launch_perlin_points(const int32_t *perm, WnPointsAoS c, size_t first, size_t count, float *out, cudaStream_t st);
+int wn_launch_perlin_lattice(const int32_t *perm, WnLattice c, size_t first, size_t count, float *out, cudaStream_t st);
+int wn_launch_perlin_affine(const int32_t *perm, WnAffine c, size_t first, size_t count, float *out, cudaStream_t st);
+// texture hooks: scale (double) and octave as in texture.h
+int wn_launch_wavelet_texture(WnTileView t, const float *p, size_t count, double scale, float oct2, float inv_std,
+                              float *grey, cudaStream_t st);
+int wn_launch_perlin_texture(const int32_t *perm, const float *p, size_t count, float scale_f, float oct,
+                             float *grey, cudaStream_t st);
+// stats: partial[] must hold 4*WN_STATS_BLOCKS doubles; result read back by the host
+#define WN_STATS_BLOCKS 592
+int wn_launch_stats(const float *data, size_t count, double *partial, cudaStream_t st);
+
+// ---- fast multiband lattice (wn_multiband_fast.cu) ------------------------------------------------
+// Computes the z-range [k0, k0+nk) of the lattice into out (out points at sample (0,0,k0)).
+int wn_launch_mb3d_lattice_fast(WnTileView t, WnLattice c, WnBands b, int k0, int nk, float *out, cudaStream_t st);
+
+// ---- device Gaussian fill (wn_rng.cu) ---------------------------------------------------------------
+// Fills out[0..count) with the libstdc++ normal_distribution<float>(mt19937(seed)) sequence.
+// scratch handling is internal (cudaMallocAsync on the stream).  Returns kernels launched, <0 on error.
+int wn_launch_gaussian_fill(unsigned seed, float *out, size_t count, cudaStream_t st);
