@@ -337,6 +337,7 @@ struct wn_tile {
     unsigned flags = 0;
     size_t count = 0;
     float *d = nullptr;
+    float *dpad = nullptr;               // 3D: x-padded replica for the fast lattice kernel
     bool built = false;
 };
 
@@ -344,6 +345,7 @@ static WnTileView tile_view(const wn_tile *t)
 {
     WnTileView v;
     v.N = t->d; v.n = t->n; v.pow2 = (t->n & (t->n - 1)) == 0;
+    v.Npad = t->dpad;
     return v;
 }
 
@@ -369,6 +371,15 @@ extern "C" int wn_tile_create(wn_ctx *c, int n, int dims, unsigned flags, wn_til
         delete t;
         return wn_fail(WN_ENOMEM, "cudaMalloc of the %d^%d tile failed: %s", n, dims, cudaGetErrorString(e));
     }
+    if (dims == 3) {
+        e = cudaMalloc(&t->dpad, (size_t)n * n * (n + 2) * sizeof(float));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(t->d);
+            delete t;
+            return wn_fail(WN_ENOMEM, "cudaMalloc of the padded tile failed: %s", cudaGetErrorString(e));
+        }
+    }
     *out = t;
     return WN_OK;
 }
@@ -379,7 +390,19 @@ extern "C" int wn_tile_destroy(wn_tile *t)
     DeviceGuard g(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     cudaFree(t->d);
+    cudaFree(t->dpad);
     delete t;
+    return WN_OK;
+}
+
+// the tile changed: refresh the padded replica (stream ordered) and mark it usable
+static int tile_finish(wn_tile *t)
+{
+    if (t->dpad) {
+        t->ctx->launches += (uint64_t)wn_launch_pad_tile(t->d, t->dpad, t->n, t->ctx->stream);
+        WN_CUDA(cudaGetLastError());
+    }
+    t->built = true;
     return WN_OK;
 }
 
@@ -422,8 +445,7 @@ static int tile_build_device(wn_tile *t, const float *dR)
     WN_CUDA(cudaGetLastError());
     WN_CUDA(cudaFreeAsync(t1, st));
     WN_CUDA(cudaFreeAsync(t2, st));
-    t->built = true;
-    return WN_OK;
+    return tile_finish(t);
 bad:
     cudaFreeAsync(t1, st); cudaFreeAsync(t2, st);
     return wn_fail(WN_EINVAL, "tile size %d does not fit the filter kernels' shared memory", t->n);
@@ -467,8 +489,9 @@ extern "C" int wn_tile_upload(wn_tile *t, const float *N, int space)
     DeviceGuard g(t->ctx->device);
     WN_CUDA(cudaMemcpyAsync(t->d, N, t->count * sizeof(float),
                             space == WN_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, t->ctx->stream));
+    int r = tile_finish(t);
+    if (r) return r;
     if (space != WN_DEVICE) WN_CUDA(cudaStreamSynchronize(t->ctx->stream));
-    t->built = true;
     return WN_OK;
 }
 
@@ -493,8 +516,8 @@ extern "C" int wn_tile_device_ptr(const wn_tile *t, void **dptr)
 extern "C" int wn_tile_mark_built(wn_tile *t)
 {
     WN_REQUIRE(t, "wn_tile_mark_built: tile is NULL");
-    t->built = true;
-    return WN_OK;
+    DeviceGuard g(t->ctx->device);
+    return tile_finish(t);
 }
 
 #define WN_NEED_TILE(t, d, who)                                                                    \
@@ -656,12 +679,12 @@ extern "C" int wn_multiband3d_lattice(const wn_tile *t, const float *xs, int nx,
         });
     }
     if (space == WN_DEVICE)
-        return run_device(c, [&](cudaStream_t st) { return wn_launch_mb3d_lattice_fast(tv, L, b, 0, nz, out, st); });
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_mb3d_lattice_fast(tv, L, ys, zs, b, 0, nz, out, st); });
     // HOST: chunk by whole z slices so each chunk is a lattice slab
     size_t slices_per_chunk = std::max<size_t>(1, kChunkSamples / slice);
     ChunkIO io; io.out = out; io.out_item = slice * sizeof(float);
     return run_chunked_host(c, (size_t)nz, slices_per_chunk, io, [&](void *, void *, float *dout, size_t first, size_t cnt, cudaStream_t st) {
-        return wn_launch_mb3d_lattice_fast(tv, L, b, (int)first, (int)cnt, dout, st);
+        return wn_launch_mb3d_lattice_fast(tv, L, ys, zs, b, (int)first, (int)cnt, dout, st);
     });
 }
 

@@ -37,6 +37,7 @@ struct WnTileView {
     const float *N;
     int n;                      // tile edge
     int pow2;                   // n is a power of two -> Mod is a mask
+    const float *Npad;          // 3D only: rows padded to n+2 floats, [x = n, n+1] repeat [x = 0, 1] (fast lattice kernel)
 };
 
 // ---- tile construction (wn_tilegen.cu) ------------------------------------------------------------
@@ -72,7 +73,12 @@ int wn_launch_stats(const float *data, size_t count, double *partial, cudaStream
 
 // ---- fast multiband lattice (wn_multiband_fast.cu) ------------------------------------------------
 // Computes the z-range [k0, k0+nk) of the lattice into out (out points at sample (0,0,k0)).
-int wn_launch_mb3d_lattice_fast(WnTileView t, WnLattice c, WnBands b, int k0, int nk, float *out, cudaStream_t st);
+// c holds DEVICE axis pointers; h_ys / h_zs are the same y / z axes on the host (used to plan the bricks).
+int wn_launch_mb3d_lattice_fast(WnTileView t, WnLattice c, const float *h_ys, const float *h_zs, WnBands b, int k0, int nk,
+                                float *out, cudaStream_t st);
+
+// 3D tile -> x-padded replica (row pitch n+2, the two extra cells wrap around)
+int wn_launch_pad_tile(const float *N, float *Npad, int n, cudaStream_t st);
 
 // ---- device Gaussian fill (wn_rng.cu) ---------------------------------------------------------------
 // Fills out[0..count) with the libstdc++ normal_distribution<float>(mt19937(seed)) sequence.
