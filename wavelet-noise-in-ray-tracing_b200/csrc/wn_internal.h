@@ -72,10 +72,20 @@ int wn_launch_perlin_texture(const int32_t *perm, const float *p, size_t count, 
 int wn_launch_stats(const float *data, size_t count, double *partial, cudaStream_t st);
 
 // ---- fast multiband lattice (wn_multiband_fast.cu) ------------------------------------------------
-// Computes the z-range [k0, k0+nk) of the lattice into out (out points at sample (0,0,k0)).
-// c holds DEVICE axis pointers; h_ys / h_zs are the same y / z axes on the host (used to plan the bricks).
-int wn_launch_mb3d_lattice_fast(WnTileView t, WnLattice c, const float *h_ys, const float *h_zs, WnBands b, int k0, int nk,
-                                float *out, cudaStream_t st);
+// prepare: decides which bands are periodic on this lattice ("folded"), evaluates their period block once.
+// run    : computes the z-range [k0, k0+nk) of the lattice into out (out points at sample (0,0,k0)).
+// finish : releases the period block.  All stream ordered on `st`.
+// c holds DEVICE axis pointers; h_xs / h_ys / h_zs are the same axes on the host (brick planning, period detection).
+struct WnFastPlan {
+    WnBands direct;             // bands evaluated per sample
+    float *P;                   // sum of the folded bands on the period block Lx x Ly x Lz, or nullptr
+    int Lx, Ly, Lz;
+};
+int  wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const float *h_ys, const float *h_zs, WnBands b,
+                          WnFastPlan *plan, cudaStream_t st);
+int  wn_mb3d_fast_run(WnTileView t, WnLattice c, const float *h_ys, const float *h_zs, const WnBands &all_bands,
+                      const WnFastPlan *plan, int k0, int nk, float *out, cudaStream_t st);
+void wn_mb3d_fast_finish(WnFastPlan *plan, cudaStream_t st);
 
 // 3D tile -> x-padded replica (row pitch n+2, the two extra cells wrap around)
 int wn_launch_pad_tile(const float *N, float *Npad, int n, cudaStream_t st);

@@ -24,9 +24,17 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace {
+
+// sum of the periodic ("folded") bands on their common period block, added by index mod period; P == nullptr: none
+struct WnFold {
+    const float *P;
+    int Lx, Ly, Lz;
+    int kphase;                 // (first z index of this launch) mod Lz
+};
 
 __device__ __forceinline__ int tmodf(int x, int n, int pow2)
 {
@@ -70,20 +78,33 @@ template <int BY, int BZ, int NT>
 __global__ void __launch_bounds__(NT)
 k_mb3d_brick(const float *__restrict__ N, int n, int pow2, const float4 *__restrict__ tabX,
              const float4 *__restrict__ tabY, const float4 *__restrict__ tabZ, int nx, int ny, int nk, int nbands,
-             int max_rows, float *__restrict__ out)
+             int max_rows, WnFold fold, float *__restrict__ out)
 {
     constexpr int NW = NT / 32;
     constexpr int C = BY / NW;                  // y columns per thread
+    constexpr int PER_BAND = 32 + BY + BZ;      // table entries of one band this brick needs
     static_assert(BY % NW == 0, "BY must be a multiple of the warp count");
-    extern __shared__ float U[];                // [Ez][Ey][32] followed by int rowoff[max_rows]
-    int *s_rowoff = reinterpret_cast<int *>(U + (size_t)max_rows * 32);
-    __shared__ float4 s_z[BZ];
+    // dynamic shared memory: U[max_rows][32] | band tables: nbands x (x[32], y[BY], z[BZ]) float4 | rowoff[max_rows]
+    // (max_rows is a multiple of 4)
+    extern __shared__ float4 smem4[];
+    float *U = reinterpret_cast<float *>(smem4);
+    const float4 *s_tab = smem4 + max_rows * 8;
+    int *s_rowoff = reinterpret_cast<int *>(smem4 + max_rows * 8 + nbands * PER_BAND);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + lane;
-    const int j0 = blockIdx.y * BY, k0 = blockIdx.z * BZ;
-    const int jl = min(j0 + BY, ny) - 1, kl = min(k0 + BZ, nk) - 1;     // last valid sample of the brick
-    const int ic = min(i, nx - 1);
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * BY, k0 = blockIdx.z * BZ;
+    const int pitch = n + 2;
+
+    // ---- phase 0: every table entry of every band in one round of independent loads
+    for (int e = threadIdx.x; e < nbands * PER_BAND; e += NT) {
+        const int b = e / PER_BAND, q = e - b * PER_BAND;
+        float4 v;
+        if (q < 32)           v = __ldg(tabX + b * nx + min(i0 + q, nx - 1));
+        else if (q < 32 + BY) v = __ldg(tabY + b * ny + min(j0 + q - 32, ny - 1));
+        else                  v = __ldg(tabZ + b * nk + min(k0 + q - 32 - BY, nk - 1));
+        smem4[max_rows * 8 + e] = v;
+    }
+    __syncthreads();
 
     float acc[C][BZ];
 #pragma unroll
@@ -92,42 +113,44 @@ k_mb3d_brick(const float *__restrict__ N, int n, int pow2, const float4 *__restr
         for (int k = 0; k < BZ; ++k) acc[c][k] = 0.0f;
 
     for (int b = 0; b < nbands; ++b) {
-        const float4 *tY = tabY + b * ny, *tZ = tabZ + b * nk;
-        const float4 tx = __ldg(tabX + b * nx + ic);
-        const int my0 = __float_as_int(__ldg(&tY[j0].w)), mz0 = __float_as_int(__ldg(&tZ[k0].w));
-        const int Ey = __float_as_int(__ldg(&tY[jl].w)) - my0 + 3;
-        const int Ez = __float_as_int(__ldg(&tZ[kl].w)) - mz0 + 3;
-        const int rows = Ey * Ez;
+        const float4 *tX = s_tab + b * PER_BAND, *tY = tX + 32, *tZ = tY + BY;
+        // clamped entries repeat the last valid one, so the last entry carries the brick's last tap cell
+        const int my0 = __float_as_int(tY[0].w), mz0 = __float_as_int(tZ[0].w);
+        const int Ey = __float_as_int(tY[BY - 1].w) - my0 + 3;
+        const int Ez = __float_as_int(tZ[BZ - 1].w) - mz0 + 3;
+        const int slab = Ey * 32;
+        const int rows = Ey * Ez, rows4 = (rows + 3) & ~3;
 
-        // row r = cz*Ey + cy of the brick's footprint -> offset of the (x-padded) tile row (wrapped y, wrapped z)
-        for (int r = threadIdx.x; r < rows; r += NT) {
-            const int cz = r / Ey, cy = r - cz * Ey;
-            s_rowoff[r] = (tmodf(mz0 + cz, n, pow2) * n + tmodf(my0 + cy, n, pow2)) * (n + 2);
+        // row r = cz*Ey + cy of the brick's footprint -> offset of the (x-padded) tile row (wrapped y, wrapped z);
+        // the table is padded to a multiple of 4 rows by repeating the last row
+        {
+            const float inv_ey = 1.0f / (float)Ey;
+            for (int r = threadIdx.x; r < rows4; r += NT) {
+                const int rr = min(r, rows - 1);
+                const int cz = (int)(((float)rr + 0.5f) * inv_ey), cy = rr - cz * Ey;   // exact: rows <= 1500
+                s_rowoff[r] = (tmodf(mz0 + cz, n, pow2) * n + tmodf(my0 + cy, n, pow2)) * pitch;
+            }
         }
-        if (threadIdx.x < BZ) s_z[threadIdx.x] = __ldg(tZ + min(k0 + (int)threadIdx.x, nk - 1));
         __syncthreads();
 
-        // ---- X pass: U[cz][cy][lane] = sum_f wx[f] * N[cz][cy][cx + f]
+        // ---- X pass: U[row][lane] = sum_f wx[f] * N[row][cx + f]; each warp takes groups of 4 consecutive rows
         {
-            // rows of the padded tile hold cells 0..n+1, so the three taps are x0, x0+1, x0+2 of one address
-            const int x0 = tmodf(__float_as_int(tx.w), n, pow2);
-            float *u = U + warp * 32 + lane;
-            int r = warp;
-            for (; r + 3 * NW < rows; r += 4 * NW, u += 4 * NW * 32) {
-                const float *q0 = N + (unsigned)(s_rowoff[r] + x0), *q1 = N + (unsigned)(s_rowoff[r + NW] + x0);
-                const float *q2 = N + (unsigned)(s_rowoff[r + 2 * NW] + x0), *q3 = N + (unsigned)(s_rowoff[r + 3 * NW] + x0);
+            const float4 tx = tX[lane];
+            // padded rows hold cells 0..n+1: the three taps are x0, x0+1, x0+2 of one address
+            const float *base = N + tmodf(__float_as_int(tx.w), n, pow2);
+            for (int r = warp * 4; r < rows4; r += NW * 4) {
+                const int4 o = *reinterpret_cast<const int4 *>(s_rowoff + r);
+                const float *q0 = base + (unsigned)o.x, *q1 = base + (unsigned)o.y;
+                const float *q2 = base + (unsigned)o.z, *q3 = base + (unsigned)o.w;
                 const float a0 = __ldg(q0), a1 = __ldg(q0 + 1), a2 = __ldg(q0 + 2);
                 const float b0 = __ldg(q1), b1 = __ldg(q1 + 1), b2 = __ldg(q1 + 2);
                 const float c0 = __ldg(q2), c1 = __ldg(q2 + 1), c2 = __ldg(q2 + 2);
                 const float d0 = __ldg(q3), d1 = __ldg(q3 + 1), d2 = __ldg(q3 + 2);
-                u[0]           = fmaf(tx.z, a2, fmaf(tx.y, a1, tx.x * a0));
-                u[NW * 32]     = fmaf(tx.z, b2, fmaf(tx.y, b1, tx.x * b0));
-                u[2 * NW * 32] = fmaf(tx.z, c2, fmaf(tx.y, c1, tx.x * c0));
-                u[3 * NW * 32] = fmaf(tx.z, d2, fmaf(tx.y, d1, tx.x * d0));
-            }
-            for (; r < rows; r += NW, u += NW * 32) {
-                const float *q0 = N + (unsigned)(s_rowoff[r] + x0);
-                u[0] = fmaf(tx.z, __ldg(q0 + 2), fmaf(tx.y, __ldg(q0 + 1), tx.x * __ldg(q0)));
+                float *u = U + r * 32 + lane;                  // rows past `rows` are scratch (max_rows % 4 == 0)
+                u[0]  = fmaf(tx.z, a2, fmaf(tx.y, a1, tx.x * a0));
+                u[32] = fmaf(tx.z, b2, fmaf(tx.y, b1, tx.x * b0));
+                u[64] = fmaf(tx.z, c2, fmaf(tx.y, c1, tx.x * c0));
+                u[96] = fmaf(tx.z, d2, fmaf(tx.y, d1, tx.x * d0));
             }
         }
         __syncthreads();
@@ -139,15 +162,14 @@ k_mb3d_brick(const float *__restrict__ N, int n, int pow2, const float4 *__restr
             float v[C][3];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                ty[c] = __ldg(tY + min(j0 + warp + c * NW, ny - 1));
-                ucol[c] = U + (__float_as_int(ty[c].w) - my0) * 32 + lane + 2 * Ey * 32;
+                ty[c] = tY[warp + c * NW];
+                ucol[c] = U + (__float_as_int(ty[c].w) - my0) * 32 + lane + 2 * slab;
                 v[c][0] = v[c][1] = v[c][2] = 0.0f;
             }
-            const int slab = Ey * 32;
             int base = -3;                       // window holds V[base .. base+2]
 #pragma unroll
             for (int k = 0; k < BZ; ++k) {
-                const float4 tz = s_z[k];
+                const float4 tz = tZ[k];
                 const int rel = __float_as_int(tz.w) - mz0;
                 while (base < rel) {
                     ++base;
@@ -165,23 +187,38 @@ k_mb3d_brick(const float *__restrict__ N, int n, int pow2, const float4 *__restr
                     acc[c][k] = fmaf(tz.x, v[c][0], fmaf(tz.y, v[c][1], fmaf(tz.z, v[c][2], acc[c][k])));
             }
         }
-        __syncthreads();
+        if (b + 1 < nbands) __syncthreads();
     }
 
+    const int i = i0 + lane;
     if (i < nx) {
         const size_t plane = (size_t)nx * ny;
+        // periodic bands were evaluated once on their period block (see fold_bands): add them by index mod period
+        const float *pcol = nullptr;
+        int kz = 0;
+        if (fold.P) { pcol = fold.P + (i % fold.Lx); kz = (fold.kphase + k0) % fold.Lz; }
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = j0 + warp + c * NW;
             if (j >= ny) continue;
             float *o = out + ((size_t)i + (size_t)nx * j + plane * k0);
+            if (fold.P) {
+                const float *pj = pcol + (size_t)(j % fold.Ly) * fold.Lx;
+                const size_t pplane = (size_t)fold.Lx * fold.Ly;
+                int kk = kz;
+#pragma unroll
+                for (int k = 0; k < BZ; ++k) {
+                    acc[c][k] += __ldg(pj + pplane * kk);
+                    if (++kk == fold.Lz) kk = 0;
+                }
+            }
             if (k0 + BZ <= nk) {
 #pragma unroll
-                for (int k = 0; k < BZ; ++k) o[plane * k] = acc[c][k];
+                for (int k = 0; k < BZ; ++k) __stcs(o + plane * k, acc[c][k]);
             } else {
 #pragma unroll
                 for (int k = 0; k < BZ; ++k)
-                    if (k0 + k < nk) o[plane * k] = acc[c][k];
+                    if (k0 + k < nk) __stcs(o + plane * k, acc[c][k]);
             }
         }
     }
@@ -255,24 +292,140 @@ BrickPlan plan_bricks(const float *ys, int ny, const float *zs, int nk, const Wn
         long long ey = 0, ez = 0;
         for (int j0 = 0; j0 < ny; j0 += BY) ey = std::max<long long>(ey, (long long)my[std::min(j0 + BY, ny) - 1] - my[j0] + 3);
         for (int k0 = 0; k0 < nk; k0 += BZ) ez = std::max<long long>(ez, (long long)mz[std::min(k0 + BZ, nk) - 1] - mz[k0] + 3);
-        if (ey * ez > 1500) { p.ok = false; return p; }                 // 1500 rows * 132 B = 198 KB
-        p.max_rows = std::max(p.max_rows, (int)(ey * ez));
+        if (ey * ez > 1500) { p.ok = false; return p; }                 // 1500 rows * 128 B = 192 KB
+        p.max_rows = std::max(p.max_rows, (int)((ey * ez + 3) & ~3LL));
     }
-    p.smem = (size_t)p.max_rows * (32 * sizeof(float) + sizeof(int));
+    p.smem = (size_t)p.max_rows * (32 * sizeof(float) + sizeof(int)) + (size_t)b.nbands * (32 + BY + BZ) * sizeof(float4);
     return p;
 }
 
 template <int BY, int BZ, int NT>
 int launch_brick(WnTileView t, const float4 *tx, const float4 *ty, const float4 *tz, int nx, int ny, int nk, int nbands,
-                 float *out, const BrickPlan &plan, cudaStream_t st)
+                 float *out, const BrickPlan &plan, WnFold fold, cudaStream_t st)
 {
     auto kern = k_mb3d_brick<BY, BZ, NT>;
     const size_t smem = plan.smem;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     dim3 grid((nx + 31) / 32, (ny + BY - 1) / BY, (nk + BZ - 1) / BZ);
-    kern<<<grid, NT, smem, st>>>(t.Npad, t.n, t.pow2, tx, ty, tz, nx, ny, nk, nbands, plan.max_rows, out);
+    kern<<<grid, NT, smem, st>>>(t.Npad, t.n, t.pow2, tx, ty, tz, nx, ny, nk, nbands, plan.max_rows, fold, out);
     return 1;
+}
+
+// brick shapes (BY, BZ, threads); WN_BRICK=<index> overrides the default for tuning runs
+struct Shape { int by, bz, nt; };
+const Shape kShapes[] = { {16, 8, 256}, {16, 16, 256}, {8, 8, 256}, {8, 16, 256}, {32, 8, 256}, {16, 4, 256}, {16, 8, 512},
+                          {16, 4, 512}, {32, 4, 512}, {32, 8, 512}, {32, 4, 1024}, {16, 2, 256}, {32, 4, 256}, {32, 2, 512} };
+const int kNumShapes = (int)(sizeof(kShapes) / sizeof(kShapes[0]));
+const int kDefaultShape = 5;
+
+// -1: choose by footprint (larger bricks while several CTAs still fit an SM)
+int forced_shape()
+{
+    if (const char *e = getenv("WN_BRICK")) {
+        const int pick = atoi(e);
+        if (pick >= 0 && pick < kNumShapes) return pick;
+    }
+    return -1;
+}
+
+// One brick-kernel pass over the lattice (device axes dx/dy/dz, host copies hy/hz for planning): tables + kernel.
+// Returns kernels launched, or -1 when the lattice does not qualify (unsorted y/z, footprint too large, ...).
+int brick_pass(WnTileView t, const float *dx, const float *dy, const float *dz, const float *hy, const float *hz,
+               int nx, int ny, int nk, const WnBands &b, WnFold fold, float *out, cudaStream_t st)
+{
+    int pick = forced_shape();
+    BrickPlan plan{false, 0, 0};
+    if (pick < 0) {
+        pick = 0;                                              // 32 x 16 x 8 samples
+        plan = plan_bricks(hy, ny, hz, nk, b, kShapes[0].by, kShapes[0].bz);
+        if (!plan.ok || plan.smem > 56 * 1024) {               // big footprints: halve the brick in z
+            pick = kDefaultShape;
+            plan = plan_bricks(hy, ny, hz, nk, b, kShapes[pick].by, kShapes[pick].bz);
+        }
+    } else {
+        plan = plan_bricks(hy, ny, hz, nk, b, kShapes[pick].by, kShapes[pick].bz);
+    }
+    const int BY = kShapes[pick].by, BZ = kShapes[pick].bz;
+    const bool grid_ok = (ny + BY - 1) / BY <= 65535 && (nk + BZ - 1) / BZ <= 65535;
+    if (!plan.ok || !grid_ok || plan.smem > 200 * 1024) return -1;
+    int launches = 0;
+    const size_t per_band = (size_t)nx + ny + nk;
+    float4 *tab = nullptr;
+    if (cudaMallocAsync(&tab, (per_band * b.nbands + 1) * sizeof(float4), st) != cudaSuccess) return -1;
+    float4 *tx = tab, *ty = tab + (size_t)b.nbands * nx, *tz = ty + (size_t)b.nbands * ny;
+    if (b.nbands > 0) {
+        const int total = (int)(per_band * b.nbands);
+        WnLattice c{dx, dy, dz, nx, ny, nk};
+        k_axis_tables<<<std::min((total + 255) / 256, 1184), 256, 0, st>>>(c, b, 0, nk, tx, ty, tz);
+        ++launches;
+    }
+    int r = -1;
+#define WN_BRICK_CASE(idx, by, bz, nt) \
+    case idx: r = launch_brick<by, bz, nt>(t, tx, ty, tz, nx, ny, nk, b.nbands, out, plan, fold, st); break;
+    switch (pick) {
+        WN_BRICK_CASE(0, 16, 8, 256)  WN_BRICK_CASE(1, 16, 16, 256) WN_BRICK_CASE(2, 8, 8, 256)
+        WN_BRICK_CASE(3, 8, 16, 256)  WN_BRICK_CASE(4, 32, 8, 256)  WN_BRICK_CASE(5, 16, 4, 256)
+        WN_BRICK_CASE(6, 16, 8, 512)  WN_BRICK_CASE(7, 16, 4, 512)  WN_BRICK_CASE(8, 32, 4, 512)
+        WN_BRICK_CASE(9, 32, 8, 512)  WN_BRICK_CASE(10, 32, 4, 1024) WN_BRICK_CASE(11, 16, 2, 256)
+        WN_BRICK_CASE(12, 32, 4, 256) WN_BRICK_CASE(13, 32, 2, 512)
+    }
+#undef WN_BRICK_CASE
+    cudaFreeAsync(tab, st);
+    return r < 0 ? -1 : launches + r;
+}
+
+// ---- periodic folding ---------------------------------------------------------------------------------------
+// The tile is periodic (n cells), so whenever a band's sample lattice is commensurate with it -- coordinate i+P
+// lands on the same cell (mod n) with bit-identical weights as coordinate i -- that band's contribution repeats
+// with period P along the axis.  Such bands are evaluated once on their common period block (Lx x Ly x Lz samples,
+// by the same brick kernel) and added by index mod period in the main kernel's epilogue.  Detection is exact
+// (bitwise on the table entries the device will compute), so arbitrary coordinates simply do not fold.
+struct HostEntry {
+    float w0, w1, w2;
+    int cell;
+    bool operator==(const HostEntry &o) const
+    {
+        return std::memcmp(&w0, &o.w0, 3 * sizeof(float)) == 0 && cell == o.cell;
+    }
+};
+
+inline HostEntry host_entry(float coord, float scale, int n)          // mirrors axis_entry(), cell reduced mod n
+{
+    const float a = coord * scale - 0.5f;
+    const int mid = (int)std::ceil(a);
+    const float tt = (float)mid - a;
+    HostEntry e;
+    e.w0 = tt * tt * 0.5f;
+    const float s1 = 1.0f - tt;
+    e.w2 = s1 * s1 * 0.5f;
+    e.w1 = 1.0f - e.w0 - e.w2;
+    int m = (mid - 1) % n;
+    e.cell = m < 0 ? m + n : m;
+    return e;
+}
+
+// smallest P <= len/2 with entry[i+P] == entry[i] for all i; len when the axis is not periodic
+int axis_period(const float *xs, int len, float scale, int n)
+{
+    if (len < 4) return len;
+    std::vector<HostEntry> e(len);
+    for (int i = 0; i < len; ++i) e[i] = host_entry(xs[i], scale, n);
+    for (int P = 1; P <= len / 2; ++P) {
+        if (!(e[P] == e[0])) continue;
+        bool ok = true;
+        for (int i = 0; i + P < len && ok; ++i) ok = e[i + P] == e[i];
+        if (ok) return P;
+    }
+    return len;
+}
+
+long long lcm_capped(long long a, long long b, long long cap)
+{
+    long long x = a, y = b;
+    while (y) { long long r = x % y; x = y; y = r; }
+    const long long l = a / x * b;
+    return l > cap ? cap + 1 : l;
 }
 
 } // namespace
@@ -283,52 +436,89 @@ int wn_launch_pad_tile(const float *N, float *Npad, int n, cudaStream_t st)
     return 1;
 }
 
-int wn_launch_mb3d_lattice_fast(WnTileView t, WnLattice c, const float *h_ys, const float *h_zs, WnBands b, int k0, int nk,
-                                float *out, cudaStream_t st)
+// A fast-lattice call = prepare (fold decision on the WHOLE lattice + evaluation of the period block, once),
+// any number of z-slab launches (the chunks of a WN_HOST call), finish.  Deciding per call, not per slab, keeps
+// the result of a sample independent of how the call is chunked.
+int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const float *h_ys, const float *h_zs, WnBands b,
+                         WnFastPlan *plan, cudaStream_t st)
+{
+    plan->direct = b;
+    plan->P = nullptr;
+    plan->Lx = plan->Ly = plan->Lz = 1;
+    const int nx = c.nx, ny = c.ny, nz = c.nz;
+    if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
+    const long long total = (long long)nx * ny * nz;
+    long long budget = 1LL << 22;                              // samples in the period block (16 MiB of floats)
+    if (const char *e = getenv("WN_FOLD_BUDGET")) budget = atoll(e);
+    struct Cand { int band; int px, py, pz; long long vol; };
+    std::vector<Cand> cand;
+    if (budget > 0)
+        for (int i = 0; i < b.nbands; ++i) {
+            Cand cd{i, axis_period(h_xs, nx, b.scale[i], t.n), axis_period(h_ys, ny, b.scale[i], t.n),
+                    axis_period(h_zs, nz, b.scale[i], t.n), 0};
+            cd.vol = (long long)cd.px * cd.py * cd.pz;
+            if (cd.vol * 4 <= total) cand.push_back(cd);
+        }
+    std::sort(cand.begin(), cand.end(), [](const Cand &a, const Cand &b2) { return a.vol < b2.vol; });
+    long long Lx = 1, Ly = 1, Lz = 1;
+    bool folded[WN_MAX_BANDS] = { false };
+    int nfold = 0;
+    for (const Cand &cd : cand) {
+        const long long lx = lcm_capped(Lx, cd.px, nx), ly = lcm_capped(Ly, cd.py, ny), lz = lcm_capped(Lz, cd.pz, nz);
+        if (lx > nx || ly > ny || lz > nz) continue;
+        if (lx * ly * lz > budget || lx * ly * lz * 4 > total) continue;
+        Lx = lx; Ly = ly; Lz = lz;
+        folded[cd.band] = true;
+        ++nfold;
+    }
+    if (nfold == 0) return 0;
+    WnBands bf = b, bd = b;
+    bf.nbands = bd.nbands = 0;
+    for (int i = 0; i < b.nbands; ++i) {
+        WnBands &dst = folded[i] ? bf : bd;
+        dst.scale[dst.nbands] = b.scale[i];
+        dst.weight[dst.nbands] = b.weight[i];
+        ++dst.nbands;
+    }
+    float *P = nullptr;
+    if (cudaMallocAsync(&P, (size_t)(Lx * Ly * Lz) * sizeof(float), st) != cudaSuccess) return -1;
+    const int r = brick_pass(t, c.xs, c.ys, c.zs, h_ys, h_zs, (int)Lx, (int)Ly, (int)Lz, bf, WnFold{nullptr, 1, 1, 1, 0}, P, st);
+    if (r < 0) {                                               // period block does not qualify: evaluate everything directly
+        cudaFreeAsync(P, st);
+        return 0;
+    }
+    plan->direct = bd;
+    plan->P = P; plan->Lx = (int)Lx; plan->Ly = (int)Ly; plan->Lz = (int)Lz;
+    return r;
+}
+
+void wn_mb3d_fast_finish(WnFastPlan *plan, cudaStream_t st)
+{
+    if (plan->P) cudaFreeAsync(plan->P, st);
+    plan->P = nullptr;
+}
+
+int wn_mb3d_fast_run(WnTileView t, WnLattice c, const float *h_ys, const float *h_zs, const WnBands &all_bands,
+                     const WnFastPlan *plan, int k0, int nk, float *out, cudaStream_t st)
 {
     if (nk <= 0 || c.nx <= 0 || c.ny <= 0) return 0;
-    int launches = 0;
-    const size_t per_band = (size_t)c.nx + c.ny + nk;
+    const int nx = c.nx, ny = c.ny;
+    const float *dz = c.zs + k0, *hz = h_zs + k0;
+    const WnFold fold{plan->P, plan->Lx, plan->Ly, plan->Lz, plan->P ? k0 % plan->Lz : 0};
+    const int r = brick_pass(t, c.xs, c.ys, dz, h_ys, hz, nx, ny, nk, plan->direct, fold, out, st);
+    if (r >= 0) return r;
+
+    // ---- generic path (unsorted y/z axes or huge steps): every band by direct gathers, no folding
+    if (ny > 65535 || nk > 65535) return -1;                 // lattices that large are rejected
+    const WnBands &b = all_bands;
+    const size_t per_band = (size_t)nx + ny + nk;
     float4 *tab = nullptr;
     if (cudaMallocAsync(&tab, per_band * b.nbands * sizeof(float4), st) != cudaSuccess) return -1;
-    float4 *tx = tab, *ty = tab + (size_t)b.nbands * c.nx, *tz = ty + (size_t)b.nbands * c.ny;
-    {
-        const int total = (int)(per_band * b.nbands);
-        k_axis_tables<<<std::min((total + 255) / 256, 1184), 256, 0, st>>>(c, b, k0, nk, tx, ty, tz);
-        ++launches;
-    }
-    // brick shapes (BY, BZ, threads); WN_BRICK=<index> overrides the default for tuning runs
-    struct Shape { int by, bz; };
-    static const Shape shapes[] = { {16, 8}, {16, 16}, {8, 8}, {8, 16}, {32, 8}, {16, 4} };
-    int pick = 0;
-    if (const char *e = getenv("WN_BRICK")) pick = atoi(e);
-    if (pick < 0 || pick >= (int)(sizeof(shapes) / sizeof(shapes[0]))) pick = 0;
-    const int BY = shapes[pick].by, BZ = shapes[pick].bz;
-    const BrickPlan plan = plan_bricks(h_ys, c.ny, h_zs + k0, nk, b, BY, BZ);
-    const bool grid_ok = (c.ny + BY - 1) / BY <= 65535 && (nk + BZ - 1) / BZ <= 65535;
-    if (plan.ok && grid_ok && plan.smem <= 200 * 1024) {
-        int r = -1;
-        switch (pick) {
-        case 0: r = launch_brick<16, 8, 256>(t, tx, ty, tz, c.nx, c.ny, nk, b.nbands, out, plan, st); break;
-        case 1: r = launch_brick<16, 16, 256>(t, tx, ty, tz, c.nx, c.ny, nk, b.nbands, out, plan, st); break;
-        case 2: r = launch_brick<8, 8, 256>(t, tx, ty, tz, c.nx, c.ny, nk, b.nbands, out, plan, st); break;
-        case 3: r = launch_brick<8, 16, 256>(t, tx, ty, tz, c.nx, c.ny, nk, b.nbands, out, plan, st); break;
-        case 4: r = launch_brick<32, 8, 256>(t, tx, ty, tz, c.nx, c.ny, nk, b.nbands, out, plan, st); break;
-        case 5: r = launch_brick<16, 4, 256>(t, tx, ty, tz, c.nx, c.ny, nk, b.nbands, out, plan, st); break;
-        }
-        if (r < 0) { cudaFreeAsync(tab, st); return -1; }
-        launches += r;
-    } else {
-        // gridDim.y/z are limited to 65535: walk y and z in slabs
-        for (int kk = 0; kk < nk; kk += 65535)
-            for (int jj = 0; jj < c.ny; jj += 65535) {
-                const int cz = std::min(nk - kk, 65535), cy = std::min(c.ny - jj, 65535);
-                if (cy != c.ny || cz != nk) { cudaFreeAsync(tab, st); return -1; }    // lattices that large are rejected
-                dim3 grid((c.nx + 255) / 256, cy, cz);
-                k_mb3d_gather<<<grid, 256, 0, st>>>(t, tx, ty, tz, c.nx, c.ny, nk, b.nbands, out);
-                ++launches;
-            }
-    }
+    float4 *tx = tab, *ty = tab + (size_t)b.nbands * nx, *tz = ty + (size_t)b.nbands * ny;
+    const int total_e = (int)(per_band * b.nbands);
+    k_axis_tables<<<std::min((total_e + 255) / 256, 1184), 256, 0, st>>>(WnLattice{c.xs, c.ys, dz, nx, ny, nk}, b, 0, nk, tx, ty, tz);
+    dim3 grid((nx + 255) / 256, ny, nk);
+    k_mb3d_gather<<<grid, 256, 0, st>>>(t, tx, ty, tz, nx, ny, nk, b.nbands, out);
     cudaFreeAsync(tab, st);
-    return launches;
+    return 2;
 }
