@@ -26,13 +26,16 @@ out = torch.empty((nz, 1024, 1024), dtype=torch.float32, device="cuda")
 ref = noise.multiband3D_lattice(ax, ax, zs[:4], scale, w, float(post), mode=wn.WN_EVAL_EXACT, device_out=True)
 torch.cuda.synchronize()
 for s in shapes:
-    os.environ["WN_BRICK"] = s
-    for _ in range(2):
+    if s == "auto":
+        os.environ.pop("WN_BRICK", None)
+    else:
+        os.environ["WN_BRICK"] = s
+    for _ in range(3):
         noise.multiband3D_lattice(ax, ax, zs, scale, w, float(post), out=out)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    reps = 5
+    reps = 20
     for _ in range(reps):
         noise.multiband3D_lattice(ax, ax, zs, scale, w, float(post), out=out)
     b.record()
@@ -41,8 +44,9 @@ for s in shapes:
     err = float((out[:4] - ref).abs().max())
     print(f"WN_BRICK={s}: {ms:8.3f} ms  {1024 * 1024 * nz / ms / 1e6:8.2f} Gsamples/s  max|fast-exact|={err:.3g}", flush=True)
 # per-band cost (single band at a time)
-os.environ["WN_BRICK"] = shapes[0]
-for bi in range(len(scale)):
+if shapes[0] != "auto":
+    os.environ["WN_BRICK"] = shapes[0]
+for bi in range(len(scale) if os.environ.get("WN_PER_BAND") else 0):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     noise.multiband3D_lattice(ax, ax, zs, scale[bi:bi + 1], w[bi:bi + 1], float(post), out=out)
     a.record()

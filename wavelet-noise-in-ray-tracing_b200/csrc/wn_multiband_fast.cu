@@ -34,7 +34,16 @@ struct WnFold {
     const float *P;
     int Lx, Ly, Lz;
     int kphase;                 // (first z index of this launch) mod Lz
+    int xmask, ymask;           // L-1 when L is a power of two, else -1 (use %)
 };
+
+inline WnFold make_fold(const float *P, int Lx, int Ly, int Lz, int kphase)
+{
+    WnFold f{P, Lx, Ly, Lz, kphase, -1, -1};
+    if ((Lx & (Lx - 1)) == 0) f.xmask = Lx - 1;
+    if ((Ly & (Ly - 1)) == 0) f.ymask = Ly - 1;
+    return f;
+}
 
 __device__ __forceinline__ int tmodf(int x, int n, int pow2)
 {
@@ -74,16 +83,18 @@ __global__ void k_axis_tables(WnLattice c, WnBands b, int k0, int nk, float4 *__
     }
 }
 
-template <int BY, int BZ, int NT>
+template <int BY, int BZ, int NT, bool POW2>
 __global__ void __launch_bounds__(NT)
-k_mb3d_brick(const float *__restrict__ N, int n, int pow2, const float4 *__restrict__ tabX,
+k_mb3d_brick(const float *__restrict__ N, int n, const float4 *__restrict__ tabX,
              const float4 *__restrict__ tabY, const float4 *__restrict__ tabZ, int nx, int ny, int nk, int nbands,
              int max_rows, WnFold fold, float *__restrict__ out)
 {
     constexpr int NW = NT / 32;
     constexpr int C = BY / NW;                  // y columns per thread
     constexpr int PER_BAND = 32 + BY + BZ;      // table entries of one band this brick needs
+    constexpr int pow2 = POW2 ? 1 : 0;          // tile edge is a power of two: Mod() is a mask
     static_assert(BY % NW == 0, "BY must be a multiple of the warp count");
+    static_assert(PER_BAND <= 64 && NT % 64 == 0, "phase 0 maps 64 threads to one band");
     // dynamic shared memory: U[max_rows][32] | band tables: nbands x (x[32], y[BY], z[BZ]) float4 | rowoff[max_rows]
     // (max_rows is a multiple of 4)
     extern __shared__ float4 smem4[];
@@ -95,14 +106,18 @@ k_mb3d_brick(const float *__restrict__ N, int n, int pow2, const float4 *__restr
     const int i0 = blockIdx.x * 32, j0 = blockIdx.y * BY, k0 = blockIdx.z * BZ;
     const int pitch = n + 2;
 
-    // ---- phase 0: every table entry of every band in one round of independent loads
-    for (int e = threadIdx.x; e < nbands * PER_BAND; e += NT) {
-        const int b = e / PER_BAND, q = e - b * PER_BAND;
-        float4 v;
-        if (q < 32)           v = __ldg(tabX + b * nx + min(i0 + q, nx - 1));
-        else if (q < 32 + BY) v = __ldg(tabY + b * ny + min(j0 + q - 32, ny - 1));
-        else                  v = __ldg(tabZ + b * nk + min(k0 + q - 32 - BY, nk - 1));
-        smem4[max_rows * 8 + e] = v;
+    // ---- phase 0: every table entry of every band in one round of independent loads (64 threads per band)
+    {
+        const int q = threadIdx.x & 63;
+        for (int b = threadIdx.x >> 6; b < nbands; b += NT / 64) {
+            if (q < PER_BAND) {
+                float4 v;
+                if (q < 32)           v = __ldg(tabX + b * nx + min(i0 + q, nx - 1));
+                else if (q < 32 + BY) v = __ldg(tabY + b * ny + min(j0 + q - 32, ny - 1));
+                else                  v = __ldg(tabZ + b * nk + min(k0 + q - 32 - BY, nk - 1));
+                smem4[max_rows * 8 + b * PER_BAND + q] = v;
+            }
+        }
     }
     __syncthreads();
 
@@ -193,32 +208,221 @@ k_mb3d_brick(const float *__restrict__ N, int n, int pow2, const float4 *__restr
     const int i = i0 + lane;
     if (i < nx) {
         const size_t plane = (size_t)nx * ny;
-        // periodic bands were evaluated once on their period block (see fold_bands): add them by index mod period
-        const float *pcol = nullptr;
+        // periodic bands were evaluated once on their period block (see wn_mb3d_fast_prepare): add them by index mod period
+        const unsigned pplane = (unsigned)(fold.Lx * fold.Ly);
+        unsigned pi = 0;
         int kz = 0;
-        if (fold.P) { pcol = fold.P + (i % fold.Lx); kz = (fold.kphase + k0) % fold.Lz; }
+        if (fold.P) {
+            pi = (unsigned)(fold.xmask >= 0 ? (i & fold.xmask) : i % fold.Lx);
+            kz = fold.kphase + k0;
+            if (kz >= fold.Lz) kz %= fold.Lz;
+        }
+        const bool full = k0 + BZ <= nk;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = j0 + warp + c * NW;
             if (j >= ny) continue;
-            float *o = out + ((size_t)i + (size_t)nx * j + plane * k0);
             if (fold.P) {
-                const float *pj = pcol + (size_t)(j % fold.Ly) * fold.Lx;
-                const size_t pplane = (size_t)fold.Lx * fold.Ly;
+                const unsigned pj = pi + (unsigned)(fold.ymask >= 0 ? (j & fold.ymask) : j % fold.Ly) * (unsigned)fold.Lx;
+                if (kz + BZ <= fold.Lz) {                    // no wrap inside the brick (always true when BZ | Lz)
+                    const float *pp = fold.P + (pj + (unsigned)kz * pplane);
+#pragma unroll
+                    for (int k = 0; k < BZ; ++k) acc[c][k] += __ldg(pp + (size_t)k * pplane);
+                } else {
+                    int kk = kz;
+#pragma unroll
+                    for (int k = 0; k < BZ; ++k) {
+                        acc[c][k] += __ldg(fold.P + (pj + (unsigned)kk * pplane));
+                        if (++kk == fold.Lz) kk = 0;
+                    }
+                }
+            }
+            float *o = out + ((size_t)i + (size_t)nx * j + plane * k0);
+            if (full) {
+#pragma unroll
+                for (int k = 0; k < BZ; ++k) { __stcs(o, acc[c][k]); o += plane; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < BZ; ++k) {
+                    if (k0 + k < nk) __stcs(o, acc[c][k]);
+                    o += plane;
+                }
+            }
+        }
+    }
+}
+
+// ---- k_mb3d_brick4: same algorithm, four x-samples per thread --------------------------------------------------
+// A CTA owns 128 x BY x BZ samples; lane l owns x = 4l..4l+3, so U rows, the y-contracted window, the accumulators,
+// the period-block loads and the output stores are all float4 (LDS.128 / LDG.128 / STG.128): the per-sample FMA
+// count is unchanged but every other instruction is amortised over four samples.  Used for small footprints
+// (bands with <= ~1 cell per sample); the per-sample arithmetic is identical to k_mb3d_brick.
+template <int BY, int BZ, int NT, bool POW2>
+__global__ void __launch_bounds__(NT)
+k_mb3d_brick4(const float *__restrict__ N, int n, const float4 *__restrict__ tabX,
+              const float4 *__restrict__ tabY, const float4 *__restrict__ tabZ, int nx, int ny, int nk, int nbands,
+              int max_rows, WnFold fold, float *__restrict__ out)
+{
+    constexpr int NW = NT / 32;
+    constexpr int C = BY / NW;
+    constexpr int BX = 128;
+    constexpr int PER_BAND = BX + BY + BZ;
+    constexpr int pow2 = POW2 ? 1 : 0;
+    static_assert(BY % NW == 0, "BY must be a multiple of the warp count");
+    // dynamic shared memory (float4 units): U[max_rows][32] | tables nbands x PER_BAND | rowoff[max_rows] (int)
+    extern __shared__ float4 smem4[];
+    float4 *U4 = smem4;
+    float4 *s_tab = smem4 + max_rows * 32;
+    int *s_rowoff = reinterpret_cast<int *>(s_tab + nbands * PER_BAND);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY, k0 = blockIdx.z * BZ;
+    const int pitch = n + 2;
+
+    for (int e = threadIdx.x; e < nbands * PER_BAND; e += NT) {
+        const int b = e / PER_BAND, q = e - b * PER_BAND;
+        float4 v;
+        if (q < BX)           v = __ldg(tabX + b * nx + min(i0 + q, nx - 1));
+        else if (q < BX + BY) v = __ldg(tabY + b * ny + min(j0 + q - BX, ny - 1));
+        else                  v = __ldg(tabZ + b * nk + min(k0 + q - BX - BY, nk - 1));
+        s_tab[e] = v;
+    }
+    __syncthreads();
+
+    // ---- footprints of all bands: Ey, Ez and the first U row of each band (U holds every band at once)
+    __shared__ int s_ey[WN_MAX_BANDS], s_ez[WN_MAX_BANDS], s_row0[WN_MAX_BANDS + 1];
+    if (threadIdx.x == 0) {
+        int row0 = 0;
+        for (int b = 0; b < nbands; ++b) {
+            const float4 *tY = s_tab + b * PER_BAND + BX, *tZ = tY + BY;
+            const int ey = __float_as_int(tY[BY - 1].w) - __float_as_int(tY[0].w) + 3;
+            const int ez = __float_as_int(tZ[BZ - 1].w) - __float_as_int(tZ[0].w) + 3;
+            s_ey[b] = ey; s_ez[b] = ez; s_row0[b] = row0;
+            row0 += (ey * ez + 1) & ~1;                      // each band starts on an even row
+        }
+        s_row0[nbands] = row0;
+    }
+    __syncthreads();
+    for (int b = 0; b < nbands; ++b) {
+        const float4 *tY = s_tab + b * PER_BAND + BX, *tZ = tY + BY;
+        const int my0 = __float_as_int(tY[0].w), mz0 = __float_as_int(tZ[0].w);
+        const int Ey = s_ey[b], rows = Ey * s_ez[b], rows2 = (rows + 1) & ~1, row0 = s_row0[b];
+        const float inv_ey = 1.0f / (float)Ey;
+        for (int r = threadIdx.x; r < rows2; r += NT) {
+            const int rr = min(r, rows - 1);
+            const int cz = (int)(((float)rr + 0.5f) * inv_ey), cy = rr - cz * Ey;       // exact for rows < 2^20
+            s_rowoff[row0 + r] = (tmodf(mz0 + cz, n, pow2) * n + tmodf(my0 + cy, n, pow2)) * pitch;
+        }
+    }
+    __syncthreads();
+
+    // ---- X pass for every band: U[row][4 lanes-samples] = sum_f wx[f] * N[row][cx + f]
+    for (int b = 0; b < nbands; ++b) {
+        const float4 *tX = s_tab + b * PER_BAND;
+        const int row0 = s_row0[b], row1 = s_row0[b + 1];
+        const float4 t0 = tX[4 * lane], t1 = tX[4 * lane + 1], t2 = tX[4 * lane + 2], t3 = tX[4 * lane + 3];
+        const float *b0 = N + tmodf(__float_as_int(t0.w), n, pow2), *b1 = N + tmodf(__float_as_int(t1.w), n, pow2);
+        const float *b2 = N + tmodf(__float_as_int(t2.w), n, pow2), *b3 = N + tmodf(__float_as_int(t3.w), n, pow2);
+        for (int r = row0 + warp * 2; r < row1; r += NW * 2) {
+            const int2 o = *reinterpret_cast<const int2 *>(s_rowoff + r);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const unsigned off = (unsigned)(h ? o.y : o.x);
+                const float *q0 = b0 + off, *q1 = b1 + off, *q2 = b2 + off, *q3 = b3 + off;
+                float4 u;
+                u.x = fmaf(t0.z, __ldg(q0 + 2), fmaf(t0.y, __ldg(q0 + 1), t0.x * __ldg(q0)));
+                u.y = fmaf(t1.z, __ldg(q1 + 2), fmaf(t1.y, __ldg(q1 + 1), t1.x * __ldg(q1)));
+                u.z = fmaf(t2.z, __ldg(q2 + 2), fmaf(t2.y, __ldg(q2 + 1), t2.x * __ldg(q2)));
+                u.w = fmaf(t3.z, __ldg(q3 + 2), fmaf(t3.y, __ldg(q3 + 1), t3.x * __ldg(q3)));
+                U4[(r + h) * 32 + lane] = u;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- YZ pass for every band
+    float4 acc[C][BZ];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int k = 0; k < BZ; ++k) acc[c][k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+
+    for (int b = 0; b < nbands; ++b) {
+        const float4 *tY = s_tab + b * PER_BAND + BX, *tZ = tY + BY;
+        const int my0 = __float_as_int(tY[0].w), mz0 = __float_as_int(tZ[0].w);
+        const int slab4 = s_ey[b] * 32;                         // one cz plane of this band's U in float4 units
+        float4 ty[C];
+        const float4 *ucol[C];
+        float4 v[C][3];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            ty[c] = tY[warp + c * NW];
+            ucol[c] = U4 + s_row0[b] * 32 + (__float_as_int(ty[c].w) - my0) * 32 + lane + 2 * slab4;
+            v[c][0] = v[c][1] = v[c][2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        int base = -3;
+#pragma unroll
+        for (int k = 0; k < BZ; ++k) {
+            const float4 tz = tZ[k];
+            const int rel = __float_as_int(tz.w) - mz0;
+            while (base < rel) {
+                ++base;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float4 *uu = ucol[c] + base * slab4;
+                    const float4 u0 = uu[0], u1 = uu[32], u2 = uu[64];
+                    float4 nv;
+                    nv.x = fmaf(ty[c].z, u2.x, fmaf(ty[c].y, u1.x, ty[c].x * u0.x));
+                    nv.y = fmaf(ty[c].z, u2.y, fmaf(ty[c].y, u1.y, ty[c].x * u0.y));
+                    nv.z = fmaf(ty[c].z, u2.z, fmaf(ty[c].y, u1.z, ty[c].x * u0.z));
+                    nv.w = fmaf(ty[c].z, u2.w, fmaf(ty[c].y, u1.w, ty[c].x * u0.w));
+                    v[c][0] = v[c][1]; v[c][1] = v[c][2]; v[c][2] = nv;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float4 a = acc[c][k];
+                a.x = fmaf(tz.x, v[c][0].x, fmaf(tz.y, v[c][1].x, fmaf(tz.z, v[c][2].x, a.x)));
+                a.y = fmaf(tz.x, v[c][0].y, fmaf(tz.y, v[c][1].y, fmaf(tz.z, v[c][2].y, a.y)));
+                a.z = fmaf(tz.x, v[c][0].z, fmaf(tz.y, v[c][1].z, fmaf(tz.z, v[c][2].z, a.z)));
+                a.w = fmaf(tz.x, v[c][0].w, fmaf(tz.y, v[c][1].w, fmaf(tz.z, v[c][2].w, a.w)));
+                acc[c][k] = a;
+            }
+        }
+    }
+
+    // ---- epilogue (host guarantees nx % 4 == 0 and, when folding, Lx % 4 == 0): float4 loads and stores
+    const int i = i0 + 4 * lane;
+    if (i < nx) {
+        const size_t plane = (size_t)nx * ny;
+        const unsigned pplane = (unsigned)(fold.Lx * fold.Ly);
+        unsigned pi = 0;
+        int kz = 0;
+        if (fold.P) {
+            pi = (unsigned)(fold.xmask >= 0 ? (i & fold.xmask) : i % fold.Lx);
+            kz = fold.kphase + k0;
+            if (kz >= fold.Lz) kz %= fold.Lz;
+        }
+        const bool full = k0 + BZ <= nk;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = j0 + warp + c * NW;
+            if (j >= ny) continue;
+            if (fold.P) {
+                const unsigned pj = pi + (unsigned)(fold.ymask >= 0 ? (j & fold.ymask) : j % fold.Ly) * (unsigned)fold.Lx;
                 int kk = kz;
 #pragma unroll
                 for (int k = 0; k < BZ; ++k) {
-                    acc[c][k] += __ldg(pj + pplane * kk);
+                    const float4 pv = __ldg(reinterpret_cast<const float4 *>(fold.P + (pj + (unsigned)kk * pplane)));
+                    acc[c][k].x += pv.x; acc[c][k].y += pv.y; acc[c][k].z += pv.z; acc[c][k].w += pv.w;
                     if (++kk == fold.Lz) kk = 0;
                 }
             }
-            if (k0 + BZ <= nk) {
+            float *o = out + ((size_t)i + (size_t)nx * j + plane * k0);
 #pragma unroll
-                for (int k = 0; k < BZ; ++k) __stcs(o + plane * k, acc[c][k]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < BZ; ++k)
-                    if (k0 + k < nk) __stcs(o + plane * k, acc[c][k]);
+            for (int k = 0; k < BZ; ++k) {
+                if (full || k0 + k < nk) __stcs(reinterpret_cast<float4 *>(o), acc[c][k]);
+                o += plane;
             }
         }
     }
@@ -280,7 +484,8 @@ inline int first_cell(float coord, float scale) { return (int)std::ceil(coord * 
 
 struct BrickPlan { bool ok; size_t smem; int max_rows; };
 
-BrickPlan plan_bricks(const float *ys, int ny, const float *zs, int nk, const WnBands &b, int BY, int BZ)
+BrickPlan plan_bricks(const float *ys, int ny, const float *zs, int nk, const WnBands &b, int BY, int BZ, int BX = 32,
+                      bool all_bands_resident = false)
 {
     BrickPlan p{true, 0, 0};
     std::vector<int> my(ny), mz(nk);
@@ -292,10 +497,12 @@ BrickPlan plan_bricks(const float *ys, int ny, const float *zs, int nk, const Wn
         long long ey = 0, ez = 0;
         for (int j0 = 0; j0 < ny; j0 += BY) ey = std::max<long long>(ey, (long long)my[std::min(j0 + BY, ny) - 1] - my[j0] + 3);
         for (int k0 = 0; k0 < nk; k0 += BZ) ez = std::max<long long>(ez, (long long)mz[std::min(k0 + BZ, nk) - 1] - mz[k0] + 3);
-        if (ey * ez > 1500) { p.ok = false; return p; }                 // 1500 rows * 128 B = 192 KB
-        p.max_rows = std::max(p.max_rows, (int)((ey * ez + 3) & ~3LL));
+        if (ey * ez * BX > 1500 * 32) { p.ok = false; return p; }       // U must stay below ~192 KB
+        const int rows_b = (int)((ey * ez + 3) & ~3LL);
+        p.max_rows = all_bands_resident ? p.max_rows + rows_b : std::max(p.max_rows, rows_b);
     }
-    p.smem = (size_t)p.max_rows * (32 * sizeof(float) + sizeof(int)) + (size_t)b.nbands * (32 + BY + BZ) * sizeof(float4);
+    if ((long long)p.max_rows * BX > 1500 * 32) { p.ok = false; return p; }
+    p.smem = (size_t)p.max_rows * (BX * sizeof(float) + sizeof(int)) + (size_t)b.nbands * (BX + BY + BZ) * sizeof(float4);
     return p;
 }
 
@@ -303,19 +510,34 @@ template <int BY, int BZ, int NT>
 int launch_brick(WnTileView t, const float4 *tx, const float4 *ty, const float4 *tz, int nx, int ny, int nk, int nbands,
                  float *out, const BrickPlan &plan, WnFold fold, cudaStream_t st)
 {
-    auto kern = k_mb3d_brick<BY, BZ, NT>;
+    auto kern = t.pow2 ? k_mb3d_brick<BY, BZ, NT, true> : k_mb3d_brick<BY, BZ, NT, false>;
     const size_t smem = plan.smem;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     dim3 grid((nx + 31) / 32, (ny + BY - 1) / BY, (nk + BZ - 1) / BZ);
-    kern<<<grid, NT, smem, st>>>(t.Npad, t.n, t.pow2, tx, ty, tz, nx, ny, nk, nbands, plan.max_rows, fold, out);
+    kern<<<grid, NT, smem, st>>>(t.Npad, t.n, tx, ty, tz, nx, ny, nk, nbands, plan.max_rows, fold, out);
+    return 1;
+}
+
+template <int BY, int BZ, int NT>
+int launch_brick4(WnTileView t, const float4 *tx, const float4 *ty, const float4 *tz, int nx, int ny, int nk, int nbands,
+                  float *out, const BrickPlan &plan, WnFold fold, cudaStream_t st)
+{
+    auto kern = t.pow2 ? k_mb3d_brick4<BY, BZ, NT, true> : k_mb3d_brick4<BY, BZ, NT, false>;
+    const size_t smem = plan.smem;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    dim3 grid((nx + 127) / 128, (ny + BY - 1) / BY, (nk + BZ - 1) / BZ);
+    kern<<<grid, NT, smem, st>>>(t.Npad, t.n, tx, ty, tz, nx, ny, nk, nbands, plan.max_rows, fold, out);
     return 1;
 }
 
 // brick shapes (BY, BZ, threads); WN_BRICK=<index> overrides the default for tuning runs
 struct Shape { int by, bz, nt; };
-const Shape kShapes[] = { {16, 8, 256}, {16, 16, 256}, {8, 8, 256}, {8, 16, 256}, {32, 8, 256}, {16, 4, 256}, {16, 8, 512},
-                          {16, 4, 512}, {32, 4, 512}, {32, 8, 512}, {32, 4, 1024}, {16, 2, 256}, {32, 4, 256}, {32, 2, 512} };
+const Shape kShapes[] = { {16, 8, 256}, {16, 16, 256}, {8, 8, 256}, {8, 16, 256}, {8, 4, 256}, {16, 4, 256},
+                          /* 6..9: four x-samples per thread (k_mb3d_brick4) */
+                          {8, 8, 256}, {16, 8, 256}, {8, 16, 256}, {8, 4, 256} };
+const int kFirstShape4 = 6;
 const int kNumShapes = (int)(sizeof(kShapes) / sizeof(kShapes[0]));
 const int kDefaultShape = 5;
 
@@ -336,15 +558,25 @@ int brick_pass(WnTileView t, const float *dx, const float *dy, const float *dz, 
 {
     int pick = forced_shape();
     BrickPlan plan{false, 0, 0};
+    // the float4 kernel needs 16-byte aligned rows of the output and of the period block
+    const bool can4 = (nx % 4 == 0) && (!fold.P || fold.Lx % 4 == 0);
+    if (pick >= kFirstShape4 && !can4) pick = -1;
     if (pick < 0) {
-        pick = 0;                                              // 32 x 16 x 8 samples
-        plan = plan_bricks(hy, ny, hz, nk, b, kShapes[0].by, kShapes[0].bz);
+        if (can4) {
+            pick = kFirstShape4;                               // 128 x 8 x 8 samples, small footprints only
+            plan = plan_bricks(hy, ny, hz, nk, b, kShapes[pick].by, kShapes[pick].bz, 128, true);
+        }
+        if (!plan.ok || plan.smem > 72 * 1024) {
+            pick = 0;                                          // 32 x 16 x 8 samples
+            plan = plan_bricks(hy, ny, hz, nk, b, kShapes[0].by, kShapes[0].bz);
+        }
         if (!plan.ok || plan.smem > 56 * 1024) {               // big footprints: halve the brick in z
             pick = kDefaultShape;
             plan = plan_bricks(hy, ny, hz, nk, b, kShapes[pick].by, kShapes[pick].bz);
         }
     } else {
-        plan = plan_bricks(hy, ny, hz, nk, b, kShapes[pick].by, kShapes[pick].bz);
+        plan = plan_bricks(hy, ny, hz, nk, b, kShapes[pick].by, kShapes[pick].bz, pick >= kFirstShape4 ? 128 : 32,
+                           pick >= kFirstShape4);
     }
     const int BY = kShapes[pick].by, BZ = kShapes[pick].bz;
     const bool grid_ok = (ny + BY - 1) / BY <= 65535 && (nk + BZ - 1) / BZ <= 65535;
@@ -365,10 +597,12 @@ int brick_pass(WnTileView t, const float *dx, const float *dy, const float *dz, 
     case idx: r = launch_brick<by, bz, nt>(t, tx, ty, tz, nx, ny, nk, b.nbands, out, plan, fold, st); break;
     switch (pick) {
         WN_BRICK_CASE(0, 16, 8, 256)  WN_BRICK_CASE(1, 16, 16, 256) WN_BRICK_CASE(2, 8, 8, 256)
-        WN_BRICK_CASE(3, 8, 16, 256)  WN_BRICK_CASE(4, 32, 8, 256)  WN_BRICK_CASE(5, 16, 4, 256)
-        WN_BRICK_CASE(6, 16, 8, 512)  WN_BRICK_CASE(7, 16, 4, 512)  WN_BRICK_CASE(8, 32, 4, 512)
-        WN_BRICK_CASE(9, 32, 8, 512)  WN_BRICK_CASE(10, 32, 4, 1024) WN_BRICK_CASE(11, 16, 2, 256)
-        WN_BRICK_CASE(12, 32, 4, 256) WN_BRICK_CASE(13, 32, 2, 512)
+        WN_BRICK_CASE(3, 8, 16, 256)  WN_BRICK_CASE(4, 8, 4, 256)   WN_BRICK_CASE(5, 16, 4, 256)
+#define WN_BRICK4_CASE(idx, by, bz, nt) \
+    case idx: r = launch_brick4<by, bz, nt>(t, tx, ty, tz, nx, ny, nk, b.nbands, out, plan, fold, st); break;
+        WN_BRICK4_CASE(6, 8, 8, 256)  WN_BRICK4_CASE(7, 16, 8, 256) WN_BRICK4_CASE(8, 8, 16, 256)
+        WN_BRICK4_CASE(9, 8, 4, 256)
+#undef WN_BRICK4_CASE
     }
 #undef WN_BRICK_CASE
     cudaFreeAsync(tab, st);
@@ -482,7 +716,7 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
     }
     float *P = nullptr;
     if (cudaMallocAsync(&P, (size_t)(Lx * Ly * Lz) * sizeof(float), st) != cudaSuccess) return -1;
-    const int r = brick_pass(t, c.xs, c.ys, c.zs, h_ys, h_zs, (int)Lx, (int)Ly, (int)Lz, bf, WnFold{nullptr, 1, 1, 1, 0}, P, st);
+    const int r = brick_pass(t, c.xs, c.ys, c.zs, h_ys, h_zs, (int)Lx, (int)Ly, (int)Lz, bf, make_fold(nullptr, 1, 1, 1, 0), P, st);
     if (r < 0) {                                               // period block does not qualify: evaluate everything directly
         cudaFreeAsync(P, st);
         return 0;
@@ -504,7 +738,7 @@ int wn_mb3d_fast_run(WnTileView t, WnLattice c, const float *h_ys, const float *
     if (nk <= 0 || c.nx <= 0 || c.ny <= 0) return 0;
     const int nx = c.nx, ny = c.ny;
     const float *dz = c.zs + k0, *hz = h_zs + k0;
-    const WnFold fold{plan->P, plan->Lx, plan->Ly, plan->Lz, plan->P ? k0 % plan->Lz : 0};
+    const WnFold fold = make_fold(plan->P, plan->Lx, plan->Ly, plan->Lz, plan->P ? k0 % plan->Lz : 0);
     const int r = brick_pass(t, c.xs, c.ys, dz, h_ys, hz, nx, ny, nk, plan->direct, fold, out, st);
     if (r >= 0) return r;
 
