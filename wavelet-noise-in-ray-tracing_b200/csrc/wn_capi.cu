@@ -251,6 +251,22 @@ static int run_chunked_host(wn_ctx *c, size_t total, size_t chunk, const ChunkIO
     // the parameter block was written on c->stream; the h2d stream needs no ordering with it.
     timing_begin(c);
     size_t nchunks = (total + chunk - 1) / chunk;
+    if (nchunks == 1) {
+        // small calls (the scalar evaluate*() methods are count == 1): everything in order on the compute stream
+        if (io.in_item)
+            WN_CUDA(cudaMemcpyAsync(c->in[0].p, io.in, total * io.in_item, cudaMemcpyHostToDevice, c->stream));
+        if (io.aux_item)
+            WN_CUDA(cudaMemcpyAsync(c->aux[0].p, io.aux, total * io.aux_item, cudaMemcpyHostToDevice, c->stream));
+        int r = timing_mark(c, c->stream); if (r) return r;
+        int nl = launch(c->in[0].p, c->aux[0].p, (float *)c->outb[0].p, 0, total, c->stream);
+        if (nl < 0) return wn_fail(WN_EINVAL, "kernel launch rejected the configuration");
+        c->launches += (uint64_t)nl;
+        WN_CUDA(cudaGetLastError());
+        r = timing_mark(c, c->stream); if (r) return r;
+        WN_CUDA(cudaMemcpyAsync(io.out, c->outb[0].p, total * io.out_item, cudaMemcpyDeviceToHost, c->stream));
+        WN_CUDA(cudaStreamSynchronize(c->stream));
+        return timing_end(c);
+    }
     for (size_t ci = 0; ci < nchunks; ++ci) {
         const int s = (int)(ci & 1);
         const size_t first = ci * chunk, cnt = std::min(chunk, total - first);
