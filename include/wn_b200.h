@@ -109,8 +109,9 @@ int  wn_tile_info(const wn_tile *tile, int *n, int *dims, size_t *count, int *bu
  * subtraction on the GPU.  Arithmetic is un-fused and in the reference's summation order, so the
  * tile is bit-identical to the CPU one for the same R. */
 int  wn_tile_build_from_gaussian(wn_tile *tile, const float *R, int space);
-/* device-side fill: MT19937 + libstdc++'s polar method on the GPU, same accept/reject sequence
- * (so every variate lands in the same cell); float values differ from glibc logf by <= 1 ulp. */
+/* device-side fill: MT19937 + libstdc++'s polar method + a restatement of glibc's logf, all on the GPU; same
+ * accept/reject sequence and the same bits as `std::normal_distribution<float>` over a fresh
+ * `std::mt19937(seed)` (i.e. a freshly constructed WaveletNoise), so the tile is bit-identical. */
 int  wn_tile_build_seeded(wn_tile *tile, unsigned seed);
 /* adopt finished coefficients (e.g. a copy of a WaveletNoise object, or a cached tile) */
 int  wn_tile_upload(wn_tile *tile, const float *N, int space);

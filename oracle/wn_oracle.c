@@ -643,6 +643,57 @@ void orc_calculate_stats(const float *data, size_t count, orc_stats *out)
     out->var = (float)((sum_sq / (double)count) - (double)out->avg * out->avg);
 }
 
+/* glibc logf (sysdeps/ieee754/flt-32/e_logf.c, 2.27+; ARM optimized-routines algorithm, N = 16 table) restated.
+ * The device Gaussian fill (csrc/wn_rng.cu) carries the same constants; tests compare this function with the
+ * libm logf the reference links against, bit for bit, to pin them.  Normal positive inputs only. */
+float orc_logf_restated(float x)
+{
+    static const double invc[16] = {
+        0x1.661ec79f8f3bep+0, 0x1.571ed4aaf883dp+0, 0x1.49539f0f010bp+0, 0x1.3c995b0b80385p+0, 0x1.30d190c8864a5p+0,
+        0x1.25e227b0b8eap+0, 0x1.1bb4a4a1a343fp+0, 0x1.12358f08ae5bap+0, 0x1.0953f419900a7p+0, 0x1p+0,
+        0x1.e608cfd9a47acp-1, 0x1.ca4b31f026aap-1, 0x1.b2036576afce6p-1, 0x1.9c2d163a1aa2dp-1, 0x1.886e6037841edp-1,
+        0x1.767dcf5534862p-1 };
+    static const double logc[16] = {
+        -0x1.57bf7808caadep-2, -0x1.2bef0a7c06ddbp-2, -0x1.01eae7f513a67p-2, -0x1.b31d8a68224e9p-3, -0x1.6574f0ac07758p-3,
+        -0x1.1aa2bc79c81p-3, -0x1.a4e76ce8c0e5ep-4, -0x1.1973c5a611cccp-4, -0x1.252f438e10c1ep-5, 0x0p+0,
+        0x1.aa5aa5df25984p-5, 0x1.c5e53aa362eb4p-4, 0x1.526e57720db08p-3, 0x1.bc2860d22477p-3, 0x1.1058bc8a07ee1p-2,
+        0x1.4043057b6ee09p-2 };
+    uint32_t ix;
+    memcpy(&ix, &x, 4);
+    if (ix == 0x3f800000u) return 0.0f;
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> 19) & 15u);
+    const int k = (int32_t)tmp >> 23;
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    float zf;
+    memcpy(&zf, &iz, 4);
+    const double z = (double)zf;
+    const double r = z * invc[i] - 1;
+    const double y0 = logc[i] + (double)k * 0x1.62e42fefa39efp-1;
+    const double r2 = r * r;
+    double y = 0x1.5575b0be00b6ap-2 * r + -0x1.ffffef20a4123p-2;
+    y = -0x1.00ea348b88334p-2 * r2 + y;
+    y = y * r2 + (y0 + r);
+    return (float)y;
+}
+
+/* number of floats in [lo, hi] (bit patterns stepped by `step`) where orc_logf_restated differs from libm logf */
+uint64_t orc_logf_mismatches(float lo, float hi, uint32_t step)
+{
+    uint32_t a, b;
+    memcpy(&a, &lo, 4);
+    memcpy(&b, &hi, 4);
+    uint64_t bad = 0;
+    for (uint64_t u = a; u <= b; u += step) {
+        uint32_t uu = (uint32_t)u;
+        float x;
+        memcpy(&x, &uu, 4);
+        float p = logf(x), q = orc_logf_restated(x);
+        if (memcmp(&p, &q, 4) != 0) ++bad;
+    }
+    return bad;
+}
+
 uint64_t orc_fnv1a64(const void *bytes, size_t len)
 {
     const unsigned char *b = (const unsigned char *)bytes;

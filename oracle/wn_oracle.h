@@ -121,6 +121,8 @@ double orc_perlin_texture_value(const int32_t perm512[512], const float p[3], do
 typedef struct { float avg, var, min_val, max_val; } orc_stats;
 void orc_calculate_stats(const float *data, size_t count, orc_stats *out);
 
+float    orc_logf_restated(float x);      /* glibc logf restatement (pins the device table of csrc/wn_rng.cu) */
+uint64_t orc_logf_mismatches(float lo, float hi, uint32_t step);
 uint64_t orc_fnv1a64(const void *bytes, size_t len);
 int      orc_max_threads(void);
 void     orc_set_threads(int threads);   /* OpenMP team size for the tile sweeps */

@@ -78,6 +78,8 @@ class Oracle:
         L.orc_perlin_lattice.argtypes = [i32p, f32p, C.c_int, f32p, C.c_int, f32p, C.c_int, f32p, C.c_int]
         L.orc_calculate_stats.argtypes = [f32p, C.c_size_t, C.POINTER(OrcStats)]
         L.orc_eval3d_taps.argtypes = [C.c_int, f32p, i32p]
+        L.orc_logf_mismatches.restype = C.c_uint64
+        L.orc_logf_mismatches.argtypes = [C.c_float, C.c_float, C.c_uint32]
 
     # --- rng ---
     def rng(self, seed):
@@ -226,6 +228,9 @@ class Oracle:
     def fnv(self, arr):
         arr = np.ascontiguousarray(arr)
         return self.L.orc_fnv1a64(arr.ctypes.data_as(C.c_void_p), arr.nbytes)
+
+    def logf_mismatches(self, lo, hi, step=1):
+        return self.L.orc_logf_mismatches(lo, hi, step)
 
     def max_threads(self):
         return self.L.orc_max_threads()

@@ -88,18 +88,30 @@ def test_second_generate_continues_rng_stream(wn, oracle):
 
 
 def test_seeded_build_and_device_field(wn, oracle, tiles128):
+    """wn_tile_build_seeded: MT19937 + libstdc++ polar method + glibc-logf restatement ON THE GPU, bit-exact."""
     import torch
     w = wn.WaveletNoise(128, 12345)
     w.generate_seeded(3)
-    got = w.getNoiseCoefficients()
-    rng = tiles128[3].max() - tiles128[3].min()
-    assert np.abs(got - tiles128[3]).max() <= 1e-5 * rng
+    assert_bits(w.getNoiseCoefficients(), tiles128[3], "device-seeded 3D tile n=128")
+    w.generate_seeded(2)
+    assert_bits(w.getNoiseCoefficients(), tiles128[2], "device-seeded 2D tile n=128")
+    for n, dims, seed in ((2, 2, 1), (8, 3, 77), (30, 3, 807), (31, 2, 5), (100, 3, 4242)):
+        w = wn.WaveletNoise(n, seed)
+        w.generate_seeded(dims)
+        assert_bits(w.getNoiseCoefficients(), oracle.generate_tile(n, seed, dims), f"device-seeded n={n} dims={dims}")
     # device-resident Gaussian field in, nothing crosses PCIe
     R = oracle.gaussian_fill(oracle.rng(5), 32 ** 3)
     w = wn.WaveletNoise(32, 5)
     w.generateNoiseTile3D(field=torch.from_numpy(R).cuda())
     w.ctx.synchronize()
     assert_bits(w.getNoiseCoefficients(), oracle.tile_from_field(R, 32, 3), "device field")
+
+
+def test_seeded_build_n256(wn, oracle):
+    w = wn.WaveletNoise(256, 12345)
+    w.generate_seeded(3)
+    oracle.set_threads(0)
+    assert_bits(w.getNoiseCoefficients(), oracle.generate_tile(256, 12345, 3), "device-seeded 3D tile n=256")
 
 
 def test_odd_offset_flag_matches_paper_restatement(wn, oracle):

@@ -16,8 +16,9 @@ PTXAS_V="${WN_PTXAS_V:+-Xptxas -v}"
 ${NVCC} ${COMMON} ${PTXAS_V} -fmad=false -c "${HERE}/wn_tilegen.cu"        -o "${BUILD}/wn_tilegen.o"
 ${NVCC} ${COMMON} ${PTXAS_V} -fmad=false -c "${HERE}/wn_eval_exact.cu"     -o "${BUILD}/wn_eval_exact.o"
 ${NVCC} ${COMMON} ${PTXAS_V}             -c "${HERE}/wn_multiband_fast.cu" -o "${BUILD}/wn_multiband_fast.o"
+${NVCC} ${COMMON} ${PTXAS_V} -fmad=false -c "${HERE}/wn_rng.cu"            -o "${BUILD}/wn_rng.o"
 ${NVCC} ${COMMON}               -fmad=false -c "${HERE}/wn_capi.cu"         -o "${BUILD}/wn_capi.o"
 ${NVCC} ${ARCH} -shared -ccbin /usr/bin/g++ -o "${OUT}/libwn_b200.so" \
-    "${BUILD}/wn_tilegen.o" "${BUILD}/wn_eval_exact.o" "${BUILD}/wn_multiband_fast.o" "${BUILD}/wn_capi.o" \
+    "${BUILD}/wn_tilegen.o" "${BUILD}/wn_eval_exact.o" "${BUILD}/wn_multiband_fast.o" "${BUILD}/wn_rng.o" "${BUILD}/wn_capi.o" \
     -cudart static
 echo "built ${OUT}/libwn_b200.so"

@@ -491,12 +491,38 @@ extern "C" int wn_tile_build_from_gaussian(wn_tile *t, const float *R, int space
 extern "C" int wn_tile_build_seeded(wn_tile *t, unsigned seed)
 {
     WN_REQUIRE(t, "wn_tile_build_seeded: tile is NULL");
-    // round-1 slice: the Gaussian field comes from the reference's own host generator objects
-    // (std::mt19937 + std::normal_distribution<float>), then H2D + device filter passes.
-    std::vector<float> R(t->count);
-    wn_rng rng(seed);
-    for (size_t i = 0; i < t->count; ++i) R[i] = rng.gauss(rng.engine);
-    return wn_tile_build_from_gaussian(t, R.data(), WN_HOST);
+    wn_ctx *c = t->ctx;
+    DeviceGuard g(c->device);
+    cudaStream_t st = c->stream;
+    float *dR = nullptr;
+    unsigned long long *dacc = nullptr;
+    WN_CUDA(cudaMallocAsync(&dR, t->count * sizeof(float), st));
+    WN_CUDA(cudaMallocAsync(&dacc, sizeof(unsigned long long), st));
+    int rc = WN_OK;
+    for (int margin = 20; ; margin *= 4) {                 // 2 % more attempts than expected; never short in practice
+        timing_begin(c);
+        timing_mark(c, st);
+        const int nl = wn_launch_gaussian_fill(seed, dR, t->count, dacc, margin, st);
+        if (nl < 0) { rc = wn_fail(WN_ECUDA, "device Gaussian fill failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        c->launches += (uint64_t)nl;
+        unsigned long long accepted = 0;
+        if (cudaMemcpyAsync(&accepted, dacc, sizeof(accepted), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            rc = wn_fail(WN_ECUDA, "device Gaussian fill failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (2 * accepted >= t->count) {
+            rc = tile_build_device(t, dR);
+            timing_mark(c, st);
+            break;
+        }
+        if (margin > 2000) { rc = wn_fail(WN_ESTATE, "device Gaussian fill could not accept enough attempts"); break; }
+    }
+    cudaFreeAsync(dR, st);
+    cudaFreeAsync(dacc, st);
+    if (rc) return rc;
+    WN_CUDA(cudaStreamSynchronize(st));
+    return timing_end(c);
 }
 
 extern "C" int wn_tile_upload(wn_tile *t, const float *N, int space)
