@@ -94,6 +94,24 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def profiled_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch at N=1 bench size, from the
+    committed `ncu --set full` capture (profiles/r1_brick4_full_raw.csv); None when the capture is missing."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1_brick4_full_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        total = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            total += float(vals[i].replace(",", "")) * scale[units[i]]
+        return total
+    except (OSError, ValueError, KeyError, IndexError):
+        return None
+
+
 def config3(wnsh):
     ax = wnsh.lattice_axes_config3(VOLUME)
     scale, w, post = wnsh.config3_bands(4, 8)
@@ -260,7 +278,9 @@ def run_ours(args, rank, world, local_rank):
     roofline = {
         "bound": "hbm", "kernel": "k_mb3d_brick4 (multiband lattice, all launches of one step)",
         "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-        "peak_source": peak_src, "traffic": None,
+        "peak_source": peak_src,
+        "traffic": profiled_traffic_bytes() if world == 1 else None,
+        "traffic_source": "profiles/r1_brick4_full_raw.csv (ncu --set full, one launch at N=1 bench size)",
         "algorithmic_bytes_per_launch": samples_local * OUT_BYTES_PER_SAMPLE + TILE_N ** 3 * 4,
         "launch_ms": med_launch_ms,
         "fp32": {"flop_per_sample": FLOP_PER_SAMPLE,
@@ -335,7 +355,18 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        # NCCL prints its version banner on stdout at communicator creation: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     try:
         run_ours(args, rank, world, local_rank)
     finally:
