@@ -561,6 +561,11 @@ int brick_pass(WnTileView t, const float *dx, const float *dy, const float *dz, 
     // the float4 kernel needs 16-byte aligned rows of the output and of the period block
     const bool can4 = (nx % 4 == 0) && (!fold.P || fold.Lx % 4 == 0);
     if (pick >= kFirstShape4 && !can4) pick = -1;
+    if (pick >= 0) {                                           // forced shape (tuning): only where it fits
+        plan = plan_bricks(hy, ny, hz, nk, b, kShapes[pick].by, kShapes[pick].bz, pick >= kFirstShape4 ? 128 : 32,
+                           pick >= kFirstShape4);
+        if (!plan.ok || plan.smem > 100 * 1024) pick = -1;
+    }
     if (pick < 0) {
         if (can4) {
             pick = kFirstShape4;                               // 128 x 8 x 8 samples, small footprints only
@@ -574,9 +579,6 @@ int brick_pass(WnTileView t, const float *dx, const float *dy, const float *dz, 
             pick = kDefaultShape;
             plan = plan_bricks(hy, ny, hz, nk, b, kShapes[pick].by, kShapes[pick].bz);
         }
-    } else {
-        plan = plan_bricks(hy, ny, hz, nk, b, kShapes[pick].by, kShapes[pick].bz, pick >= kFirstShape4 ? 128 : 32,
-                           pick >= kFirstShape4);
     }
     const int BY = kShapes[pick].by, BZ = kShapes[pick].bz;
     const bool grid_ok = (ny + BY - 1) / BY <= 65535 && (nk + BZ - 1) / BZ <= 65535;
