@@ -4,7 +4,8 @@
 1. result_raw/*.raw  -- byte copies of the 15 images the reference SHIPS in experient/result_raw
    (float32 LE, 256x256; produced by experient/main.cpp:131-168).  These are the reference's only
    golden vectors.
-2. ref_vectors.npz   -- outputs of the UNMODIFIED reference compiled by oracle/Makefile
+2. result_raytracing/*.png -- byte copies of the two renders the reference ships (config 5 parity).
+3. ref_vectors.npz   -- outputs of the UNMODIFIED reference compiled by oracle/Makefile
    (oracle/_ref/libwnref.so) on small seeded inputs: tiles for n in {8,16,30,31}, evaluate2D/3D/
    3DProjected at random / negative / half-integer / huge points, Perlin (seeds 12345 and 5489),
    the two texture::value hooks.  The GPU box has no /root/reference, so these travel as fixtures.
@@ -30,6 +31,14 @@ def main():
     for f in sorted(os.listdir(src)):
         if f.endswith(".raw"):
             shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+
+    # the two renders the reference ships (result_raytracing/*.png, 1000x500, 100 spp; main.cpp:80-215)
+    dstp = os.path.join(HERE, "result_raytracing")
+    os.makedirs(dstp, exist_ok=True)
+    srcp = os.path.join(REF, "result_raytracing")
+    for f in sorted(os.listdir(srcp)):
+        if f.endswith(".png"):
+            shutil.copyfile(os.path.join(srcp, f), os.path.join(dstp, f))
 
     ref = RefLib()
     rs = np.random.RandomState(20251018)

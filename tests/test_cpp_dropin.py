@@ -91,3 +91,18 @@ def test_cpp_scalar_surface_matches_oracle(oracle):
     assert f("perlin2d") == np.float32(oracle.perlin_noise(perm, np.float32(0.3), np.float32(0.7), 0.0))
     assert f("tex0") == np.float32(oracle.wavelet_texture_value(tile, 128, [0.5, 1.5, -2.25], 1.0, 4))
     assert f("tex1") == np.float32(oracle.wavelet_texture_value(tile, 128, [9.0, 9.5, 10.25], 1.0, 4))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("choice,name", [("1\n4\n", "raytrace_Wavelet3D_octave4.png"), ("0\n4\n", "raytrace_Perlin_octave4.png")])
+def test_deferred_renderer_reproduces_shipped_png(tmp_path, golden_dir, choice, name):
+    """Config 5: the reference scene at the shipped 1000x500 / 100 spp, noise path batched on the GPU: PNG byte-identical."""
+    exe = os.path.join(BIN, "render_deferred")
+    if not os.path.exists(exe):
+        pytest.skip("render_deferred was not built (needs the reference's RTIOW headers at build time)")
+    r = subprocess.run([exe, "--out", str(tmp_path)], input=choice, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = open(tmp_path / name, "rb").read()
+    want = open(os.path.join(golden_dir, "result_raytracing", name), "rb").read()
+    assert got == want, r.stdout[-500:]
+    assert "texture lookups" in r.stdout
