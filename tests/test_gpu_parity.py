@@ -305,3 +305,51 @@ def test_large_host_call_is_chunked_consistently(wn, gpu_tiles):
     dev = t.multiband3D_lattice(ax, ax, zs, BANDS[:2], WEIGHTS[:2], 1.0, device_out=True)
     t.ctx.synchronize()
     assert_bits(host, dev.cpu().numpy(), "chunked host vs device")
+
+
+def test_folding_non_pow2_tile_and_periods(wn, oracle):
+    """Periodic folding with a non-power-of-two tile (n=30) and non-power-of-two periods (60 / 30 / 15 samples):
+    exercises the `%` paths of the brick kernels, the float4 kernel with Lx % 4 == 0 and the scalar one otherwise."""
+    tile = oracle.generate_tile(30, 807, 3)
+    w = wn.WaveletNoise(30, 807)
+    w.generateNoiseTile3D()
+    rng = float(tile.max() - tile.min())
+    for nx, ny, nz in ((240, 120, 64), (242, 61, 33)):            # second shape: nx % 4 != 0 -> one-sample-per-lane kernel
+        xs = np.arange(nx, dtype=np.float32) * np.float32(0.5)
+        ys = np.arange(ny, dtype=np.float32) * np.float32(0.5) + np.float32(3.25)
+        zs = np.arange(nz, dtype=np.float32) * np.float32(0.5) - np.float32(7.0)
+        bs, wts = [1.0, 2.0, 4.0, 0.25], [1.0, 0.5, 0.25, 2.0]
+        want = oracle.multiband3d_lattice(tile, 30, xs, ys, zs, bs, wts, 0.7)
+        got = w.multiband3D_lattice(xs, ys, zs, bs, wts, 0.7)
+        assert np.abs(got - want).max() <= 1e-5 * rng * sum(wts) * 0.7
+        exact = w.multiband3D_lattice(xs, ys, zs, bs, wts, 0.7, mode=wn.WN_EVAL_EXACT)
+        assert_bits(exact, want, "exact lattice n=30")
+
+
+def test_sharded_slabs_reassemble_bit_exactly(wn, gpu_tiles):
+    """Config 3 z-slab sharding: the slabs 1/2/4/8 ranks would compute (each with its own call, like bench.py) are
+    bit-identical to the single-call volume (same folded band set, same per-sample arithmetic)."""
+    sh = wnpkg.load_sub("sharding")
+    t = gpu_tiles[3]
+    ax = lattice_axis(np.arange(1024))
+    zs = ax[:512:2]                                                # 256 slices, still commensurate with the tile
+    full = t.multiband3D_lattice(ax[:256], ax[:256], zs, BANDS, WEIGHTS, float(POST))
+    for world in (2, 4, 8):
+        parts = []
+        for r in range(world):
+            b, e = sh.slab_range(zs.size, r, world)
+            parts.append(t.multiband3D_lattice(ax[:256], ax[:256], zs[b:e], BANDS, WEIGHTS, float(POST)))
+        assert_bits(np.concatenate(parts, 0), full, f"{world} slabs")
+
+
+def test_argument_errors(wn, gpu_tiles):
+    t3 = gpu_tiles[3]
+    ax = lattice_axis(np.arange(8))
+    with pytest.raises(wn.WnError):
+        t3.multiband3D_lattice(ax, ax, ax, np.ones(17, np.float32), np.ones(17, np.float32))     # > 16 bands
+    with pytest.raises(ValueError):
+        t3.multiband3D_lattice(ax, ax, ax, [1.0, 2.0], [1.0])
+    with pytest.raises(wn.WnError):
+        w = wn.WaveletNoise(4, 0)
+        w.allocate(3)
+        w.evaluate3D_points(np.zeros((1, 3), np.float32))                                       # tile never built
