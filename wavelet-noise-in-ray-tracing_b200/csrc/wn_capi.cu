@@ -388,7 +388,7 @@ extern "C" int wn_tile_create(wn_ctx *c, int n, int dims, unsigned flags, wn_til
         return wn_fail(WN_ENOMEM, "cudaMalloc of the %d^%d tile failed: %s", n, dims, cudaGetErrorString(e));
     }
     if (dims == 3) {
-        e = cudaMalloc(&t->dpad, (size_t)n * n * (n + 2) * sizeof(float));
+        e = cudaMalloc(&t->dpad, (size_t)n * n * (n + WN_TILE_PAD) * sizeof(float));
         if (e != cudaSuccess) {
             cudaGetLastError();
             cudaFree(t->d);

@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #define WN_MAX_BANDS 16
+#define WN_TILE_PAD 3         // extra cells per row of the x-padded tile replica: cells n, n+1, n+2 repeat 0, 1, 2
 
 // ---- sample-coordinate generators (device pointers) ---------------------------------------------
 // Every batch kernel is "for sample s in [first, first+count): out[s-first] = op(coord(s))".
@@ -37,7 +38,7 @@ struct WnTileView {
     const float *N;
     int n;                      // tile edge
     int pow2;                   // n is a power of two -> Mod is a mask
-    const float *Npad;          // 3D only: rows padded to n+2 floats, [x = n, n+1] repeat [x = 0, 1] (fast lattice kernel)
+    const float *Npad;          // 3D only: rows padded to n+WN_TILE_PAD floats, the extra cells wrap around (fast lattice kernel)
 };
 
 // ---- tile construction (wn_tilegen.cu) ------------------------------------------------------------
@@ -87,7 +88,7 @@ int  wn_mb3d_fast_run(WnTileView t, WnLattice c, const float *h_ys, const float 
                       const WnFastPlan *plan, int k0, int nk, float *out, cudaStream_t st);
 void wn_mb3d_fast_finish(WnFastPlan *plan, cudaStream_t st);
 
-// 3D tile -> x-padded replica (row pitch n+2, the two extra cells wrap around)
+// 3D tile -> x-padded replica (row pitch n+WN_TILE_PAD, the extra cells wrap around)
 int wn_launch_pad_tile(const float *N, float *Npad, int n, cudaStream_t st);
 
 // ---- device Gaussian fill (wn_rng.cu) ---------------------------------------------------------------

@@ -104,7 +104,7 @@ k_mb3d_brick(const float *__restrict__ N, int n, const float4 *__restrict__ tabX
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = blockIdx.x * 32, j0 = blockIdx.y * BY, k0 = blockIdx.z * BZ;
-    const int pitch = n + 2;
+    const int pitch = n + WN_TILE_PAD;
 
     // ---- phase 0: every table entry of every band in one round of independent loads (64 threads per band)
     {
@@ -277,7 +277,7 @@ k_mb3d_brick4(const float *__restrict__ N, int n, const float4 *__restrict__ tab
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY, k0 = blockIdx.z * BZ;
-    const int pitch = n + 2;
+    const int pitch = n + WN_TILE_PAD;
 
     for (int e = threadIdx.x; e < nbands * PER_BAND; e += NT) {
         const int b = e / PER_BAND, q = e - b * PER_BAND;
@@ -321,20 +321,50 @@ k_mb3d_brick4(const float *__restrict__ N, int n, const float4 *__restrict__ tab
         const float4 *tX = s_tab + b * PER_BAND;
         const int row0 = s_row0[b], row1 = s_row0[b + 1];
         const float4 t0 = tX[4 * lane], t1 = tX[4 * lane + 1], t2 = tX[4 * lane + 2], t3 = tX[4 * lane + 3];
-        const float *b0 = N + tmodf(__float_as_int(t0.w), n, pow2), *b1 = N + tmodf(__float_as_int(t1.w), n, pow2);
-        const float *b2 = N + tmodf(__float_as_int(t2.w), n, pow2), *b3 = N + tmodf(__float_as_int(t3.w), n, pow2);
-        for (int r = row0 + warp * 2; r < row1; r += NW * 2) {
-            const int2 o = *reinterpret_cast<const int2 *>(s_rowoff + r);
+        const int c0 = __float_as_int(t0.w), c1 = __float_as_int(t1.w), c2 = __float_as_int(t2.w), c3 = __float_as_int(t3.w);
+        const int cmin = min(min(c0, c1), min(c2, c3)), cmax = max(max(c0, c1), max(c2, c3));
+        // Bands with <= 1/2 cell per sample: a lane's four samples touch at most the four cells cmin..cmin+3, so
+        // four loads serve all of them.  Each sample's three weights are placed on that 4-cell footprint (the
+        // unused slot is an exact 0, fmaf(0, a, x) == x), which keeps the result bit-identical to the 12-load form.
+        const bool narrow = __all_sync(0xffffffffu, cmax - cmin <= 1);
+        if (narrow) {
+            const float *base = N + tmodf(cmin, n, pow2);     // padded rows hold cells 0..n+2, so cmin+3 stays in the row
+            const bool s0 = c0 != cmin, s1 = c1 != cmin, s2 = c2 != cmin, s3 = c3 != cmin;
+            // W[e][0..3]: shifted by one slot when the sample's first cell is cmin + 1
+            const float a00 = s0 ? 0.0f : t0.x, a01 = s0 ? t0.x : t0.y, a02 = s0 ? t0.y : t0.z, a03 = s0 ? t0.z : 0.0f;
+            const float a10 = s1 ? 0.0f : t1.x, a11 = s1 ? t1.x : t1.y, a12 = s1 ? t1.y : t1.z, a13 = s1 ? t1.z : 0.0f;
+            const float a20 = s2 ? 0.0f : t2.x, a21 = s2 ? t2.x : t2.y, a22 = s2 ? t2.y : t2.z, a23 = s2 ? t2.z : 0.0f;
+            const float a30 = s3 ? 0.0f : t3.x, a31 = s3 ? t3.x : t3.y, a32 = s3 ? t3.y : t3.z, a33 = s3 ? t3.z : 0.0f;
+            for (int r = row0 + warp * 2; r < row1; r += NW * 2) {
+                const int2 o = *reinterpret_cast<const int2 *>(s_rowoff + r);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const unsigned off = (unsigned)(h ? o.y : o.x);
-                const float *q0 = b0 + off, *q1 = b1 + off, *q2 = b2 + off, *q3 = b3 + off;
-                float4 u;
-                u.x = fmaf(t0.z, __ldg(q0 + 2), fmaf(t0.y, __ldg(q0 + 1), t0.x * __ldg(q0)));
-                u.y = fmaf(t1.z, __ldg(q1 + 2), fmaf(t1.y, __ldg(q1 + 1), t1.x * __ldg(q1)));
-                u.z = fmaf(t2.z, __ldg(q2 + 2), fmaf(t2.y, __ldg(q2 + 1), t2.x * __ldg(q2)));
-                u.w = fmaf(t3.z, __ldg(q3 + 2), fmaf(t3.y, __ldg(q3 + 1), t3.x * __ldg(q3)));
-                U4[(r + h) * 32 + lane] = u;
+                for (int h = 0; h < 2; ++h) {
+                    const float *q = base + (unsigned)(h ? o.y : o.x);
+                    const float v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
+                    float4 u;
+                    u.x = fmaf(a03, v3, fmaf(a02, v2, fmaf(a01, v1, a00 * v0)));
+                    u.y = fmaf(a13, v3, fmaf(a12, v2, fmaf(a11, v1, a10 * v0)));
+                    u.z = fmaf(a23, v3, fmaf(a22, v2, fmaf(a21, v1, a20 * v0)));
+                    u.w = fmaf(a33, v3, fmaf(a32, v2, fmaf(a31, v1, a30 * v0)));
+                    U4[(r + h) * 32 + lane] = u;
+                }
+            }
+        } else {
+            const float *b0 = N + tmodf(c0, n, pow2), *b1 = N + tmodf(c1, n, pow2);
+            const float *b2 = N + tmodf(c2, n, pow2), *b3 = N + tmodf(c3, n, pow2);
+            for (int r = row0 + warp * 2; r < row1; r += NW * 2) {
+                const int2 o = *reinterpret_cast<const int2 *>(s_rowoff + r);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned off = (unsigned)(h ? o.y : o.x);
+                    const float *q0 = b0 + off, *q1 = b1 + off, *q2 = b2 + off, *q3 = b3 + off;
+                    float4 u;
+                    u.x = fmaf(t0.z, __ldg(q0 + 2), fmaf(t0.y, __ldg(q0 + 1), t0.x * __ldg(q0)));
+                    u.y = fmaf(t1.z, __ldg(q1 + 2), fmaf(t1.y, __ldg(q1 + 1), t1.x * __ldg(q1)));
+                    u.z = fmaf(t2.z, __ldg(q2 + 2), fmaf(t2.y, __ldg(q2 + 1), t2.x * __ldg(q2)));
+                    u.w = fmaf(t3.z, __ldg(q3 + 2), fmaf(t3.y, __ldg(q3 + 1), t3.x * __ldg(q3)));
+                    U4[(r + h) * 32 + lane] = u;
+                }
             }
         }
     }
@@ -430,7 +460,7 @@ k_mb3d_brick4(const float *__restrict__ N, int n, const float4 *__restrict__ tab
 
 __global__ void k_pad_tile(const float *__restrict__ N, float *__restrict__ P, int n)
 {
-    const int pitch = n + 2;
+    const int pitch = n + WN_TILE_PAD;
     const size_t total = (size_t)n * n * pitch;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const size_t row = e / pitch;
