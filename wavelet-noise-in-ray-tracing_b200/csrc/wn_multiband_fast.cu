@@ -459,181 +459,6 @@ k_mb3d_brick4(const float *__restrict__ N, int n, const float4 *__restrict__ tab
     }
 }
 
-// ---- k_mb3d_plane4: brick4 with the x AND y contractions done per tile plane ----------------------------------------
-// Same brick (128 x 8 x BZ samples, 4 x-samples per lane) and the same per-sample arithmetic as k_mb3d_brick4, but the
-// first phase hands every tile plane (band, cz) of the footprint to ONE warp: it walks the plane's rows in y order,
-// x-contracts each row into registers, keeps the last three rows in a register window and emits the y-contracted
-// value V[plane][j] for every y sample whose taps end at that row.  Shared memory then holds V (8 rows per plane)
-// instead of the x-contracted rows, so the z pass needs ONE LDS.128 per window advance instead of three plus the
-// y contraction, and the row-offset tables (and their barrier) disappear.  Shared-memory wavefronts per brick
-// drop by about a quarter, which matters because brick4 is L1/LSU-bound.
-template <int BZ, bool POW2>
-__global__ void __launch_bounds__(256)
-k_mb3d_plane4(const float *__restrict__ N, int n, const float4 *__restrict__ tabX, const float4 *__restrict__ tabY,
-              const float4 *__restrict__ tabZ, int nx, int ny, int nk, int nbands, int max_planes, WnFold fold,
-              float *__restrict__ out)
-{
-    constexpr int NT = 256, NW = 8, BX = 128, BY = 8;
-    constexpr int PER_BAND = BX + BY + BZ;
-    constexpr int pow2 = POW2 ? 1 : 0;
-    // dynamic shared memory (float4 units): V[max_planes][BY][32] | tables nbands x PER_BAND
-    extern __shared__ float4 smem4[];
-    float4 *V4 = smem4;
-    float4 *s_tab = smem4 + max_planes * BY * 32;
-    __shared__ int s_pl0[WN_MAX_BANDS + 1];            // first plane of each band
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY, k0 = blockIdx.z * BZ;
-    const int pitch = n + WN_TILE_PAD;
-
-    for (int e = threadIdx.x; e < nbands * PER_BAND; e += NT) {
-        const int b = e / PER_BAND, q = e - b * PER_BAND;
-        float4 v;
-        if (q < BX)           v = __ldg(tabX + b * nx + min(i0 + q, nx - 1));
-        else if (q < BX + BY) v = __ldg(tabY + b * ny + min(j0 + q - BX, ny - 1));
-        else                  v = __ldg(tabZ + b * nk + min(k0 + q - BX - BY, nk - 1));
-        // x entries are stored slot-major ([sample slot 0..3][lane]) so a lane's four LDS.128 are conflict-free
-        s_tab[q < BX ? b * PER_BAND + (q & 3) * 32 + (q >> 2) : e] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int p0 = 0;
-        for (int b = 0; b < nbands; ++b) {
-            const float4 *tZ = s_tab + b * PER_BAND + BX + BY;
-            s_pl0[b] = p0;
-            p0 += __float_as_int(tZ[BZ - 1].w) - __float_as_int(tZ[0].w) + 3;
-        }
-        s_pl0[nbands] = p0;
-    }
-    __syncthreads();
-
-    // ---- XY pass: one warp per tile plane
-    const int planes = s_pl0[nbands];
-    for (int u = warp; u < planes; u += NW) {
-        int b = 0;
-        while (u >= s_pl0[b + 1]) ++b;
-        const int cz = u - s_pl0[b];
-        const float4 *tX = s_tab + b * PER_BAND, *tY = tX + BX, *tZ = tY + BY;
-        const int my0 = __float_as_int(tY[0].w);
-        const int Ey = __float_as_int(tY[BY - 1].w) - my0 + 3;
-        const float *plane_base = N + (unsigned)(tmodf(__float_as_int(tZ[0].w) + cz, n, pow2) * n * pitch);
-        const float4 t0 = tX[lane], t1 = tX[32 + lane], t2 = tX[64 + lane], t3 = tX[96 + lane];
-        const int c0 = __float_as_int(t0.w), c1 = __float_as_int(t1.w), c2 = __float_as_int(t2.w), c3 = __float_as_int(t3.w);
-        const int cmin = min(min(c0, c1), min(c2, c3)), cmax = max(max(c0, c1), max(c2, c3));
-        const bool narrow = __all_sync(0xffffffffu, cmax - cmin <= 1);
-        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
-        float4 *vout = V4 + u * BY * 32 + lane;
-        int jn = 0;                                    // next y sample to emit
-        int next_rel = __float_as_int(tY[0].w) - my0 + 2;   // row at which y sample jn is complete
-        if (narrow) {
-            // four cells cmin..cmin+3 serve all four samples; weights placed on that footprint (exact zeros elsewhere)
-            const float *base = plane_base + tmodf(cmin, n, pow2);
-            const bool s0 = c0 != cmin, s1 = c1 != cmin, s2 = c2 != cmin, s3 = c3 != cmin;
-            const float a00 = s0 ? 0.0f : t0.x, a01 = s0 ? t0.x : t0.y, a02 = s0 ? t0.y : t0.z, a03 = s0 ? t0.z : 0.0f;
-            const float a10 = s1 ? 0.0f : t1.x, a11 = s1 ? t1.x : t1.y, a12 = s1 ? t1.y : t1.z, a13 = s1 ? t1.z : 0.0f;
-            const float a20 = s2 ? 0.0f : t2.x, a21 = s2 ? t2.x : t2.y, a22 = s2 ? t2.y : t2.z, a23 = s2 ? t2.z : 0.0f;
-            const float a30 = s3 ? 0.0f : t3.x, a31 = s3 ? t3.x : t3.y, a32 = s3 ? t3.y : t3.z, a33 = s3 ? t3.z : 0.0f;
-            for (int cy = 0; cy < Ey; ++cy) {
-                const float *q = base + (unsigned)(tmodf(my0 + cy, n, pow2) * pitch);
-                const float v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
-                r0 = r1; r1 = r2;
-                r2.x = fmaf(a03, v3, fmaf(a02, v2, fmaf(a01, v1, a00 * v0)));
-                r2.y = fmaf(a13, v3, fmaf(a12, v2, fmaf(a11, v1, a10 * v0)));
-                r2.z = fmaf(a23, v3, fmaf(a22, v2, fmaf(a21, v1, a20 * v0)));
-                r2.w = fmaf(a33, v3, fmaf(a32, v2, fmaf(a31, v1, a30 * v0)));
-                while (jn < BY && next_rel == cy) {
-                    const float4 ty = tY[jn];
-                    float4 nv;
-                    nv.x = fmaf(ty.z, r2.x, fmaf(ty.y, r1.x, ty.x * r0.x));
-                    nv.y = fmaf(ty.z, r2.y, fmaf(ty.y, r1.y, ty.x * r0.y));
-                    nv.z = fmaf(ty.z, r2.z, fmaf(ty.y, r1.z, ty.x * r0.z));
-                    nv.w = fmaf(ty.z, r2.w, fmaf(ty.y, r1.w, ty.x * r0.w));
-                    vout[jn * 32] = nv;
-                    ++jn;
-                    if (jn < BY) next_rel = __float_as_int(tY[jn].w) - my0 + 2;
-                }
-            }
-        } else {
-            const float *b0 = plane_base + tmodf(c0, n, pow2), *b1 = plane_base + tmodf(c1, n, pow2);
-            const float *b2 = plane_base + tmodf(c2, n, pow2), *b3 = plane_base + tmodf(c3, n, pow2);
-            for (int cy = 0; cy < Ey; ++cy) {
-                const unsigned off = (unsigned)(tmodf(my0 + cy, n, pow2) * pitch);
-                const float *q0 = b0 + off, *q1 = b1 + off, *q2 = b2 + off, *q3 = b3 + off;
-                r0 = r1; r1 = r2;
-                r2.x = fmaf(t0.z, __ldg(q0 + 2), fmaf(t0.y, __ldg(q0 + 1), t0.x * __ldg(q0)));
-                r2.y = fmaf(t1.z, __ldg(q1 + 2), fmaf(t1.y, __ldg(q1 + 1), t1.x * __ldg(q1)));
-                r2.z = fmaf(t2.z, __ldg(q2 + 2), fmaf(t2.y, __ldg(q2 + 1), t2.x * __ldg(q2)));
-                r2.w = fmaf(t3.z, __ldg(q3 + 2), fmaf(t3.y, __ldg(q3 + 1), t3.x * __ldg(q3)));
-                while (jn < BY && next_rel == cy) {
-                    const float4 ty = tY[jn];
-                    float4 nv;
-                    nv.x = fmaf(ty.z, r2.x, fmaf(ty.y, r1.x, ty.x * r0.x));
-                    nv.y = fmaf(ty.z, r2.y, fmaf(ty.y, r1.y, ty.x * r0.y));
-                    nv.z = fmaf(ty.z, r2.z, fmaf(ty.y, r1.z, ty.x * r0.z));
-                    nv.w = fmaf(ty.z, r2.w, fmaf(ty.y, r1.w, ty.x * r0.w));
-                    vout[jn * 32] = nv;
-                    ++jn;
-                    if (jn < BY) next_rel = __float_as_int(tY[jn].w) - my0 + 2;
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- Z pass: thread (lane, j = warp); one LDS.128 per window advance
-    float4 acc[BZ];
-#pragma unroll
-    for (int k = 0; k < BZ; ++k) acc[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    for (int b = 0; b < nbands; ++b) {
-        const float4 *tZ = s_tab + b * PER_BAND + BX + BY;
-        const int mz0 = __float_as_int(tZ[0].w);
-        const float4 *vcol = V4 + (s_pl0[b] * BY + warp) * 32 + lane + 2 * BY * 32;
-        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
-        int base = -3;
-#pragma unroll
-        for (int k = 0; k < BZ; ++k) {
-            const float4 tz = tZ[k];
-            const int rel = __float_as_int(tz.w) - mz0;
-            while (base < rel) {
-                ++base;
-                v0 = v1; v1 = v2; v2 = vcol[base * BY * 32];
-            }
-            float4 a = acc[k];
-            a.x = fmaf(tz.x, v0.x, fmaf(tz.y, v1.x, fmaf(tz.z, v2.x, a.x)));
-            a.y = fmaf(tz.x, v0.y, fmaf(tz.y, v1.y, fmaf(tz.z, v2.y, a.y)));
-            a.z = fmaf(tz.x, v0.z, fmaf(tz.y, v1.z, fmaf(tz.z, v2.z, a.z)));
-            a.w = fmaf(tz.x, v0.w, fmaf(tz.y, v1.w, fmaf(tz.z, v2.w, a.w)));
-            acc[k] = a;
-        }
-    }
-
-    // ---- epilogue (host guarantees nx % 4 == 0 and, when folding, Lx % 4 == 0): float4 loads and stores
-    const int i = i0 + 4 * lane, j = j0 + warp;
-    if (i < nx && j < ny) {
-        const size_t plane = (size_t)nx * ny;
-        if (fold.P) {
-            const unsigned pplane = (unsigned)(fold.Lx * fold.Ly);
-            const unsigned pj = (unsigned)(fold.xmask >= 0 ? (i & fold.xmask) : i % fold.Lx) +
-                                (unsigned)(fold.ymask >= 0 ? (j & fold.ymask) : j % fold.Ly) * (unsigned)fold.Lx;
-            int kk = fold.kphase + k0;
-            if (kk >= fold.Lz) kk %= fold.Lz;
-#pragma unroll
-            for (int k = 0; k < BZ; ++k) {
-                const float4 pv = __ldg(reinterpret_cast<const float4 *>(fold.P + (pj + (unsigned)kk * pplane)));
-                acc[k].x += pv.x; acc[k].y += pv.y; acc[k].z += pv.z; acc[k].w += pv.w;
-                if (++kk == fold.Lz) kk = 0;
-            }
-        }
-        float *o = out + ((size_t)i + (size_t)nx * j + plane * k0);
-        const bool full = k0 + BZ <= nk;
-#pragma unroll
-        for (int k = 0; k < BZ; ++k) {
-            if (full || k0 + k < nk) __stcs(reinterpret_cast<float4 *>(o), acc[k]);
-            o += plane;
-        }
-    }
-}
-
 __global__ void k_pad_tile(const float *__restrict__ N, float *__restrict__ P, int n)
 {
     const int pitch = n + WN_TILE_PAD;
@@ -688,12 +513,12 @@ k_mb3d_gather(WnTileView t, const float4 *__restrict__ tabX, const float4 *__res
 // -ffp-contract=off), monotonicity of y/z and the largest Ey*Ez any brick needs.
 inline int first_cell(float coord, float scale) { return (int)std::ceil(coord * scale - 0.5f) - 1; }
 
-struct BrickPlan { bool ok; size_t smem; int max_rows; int sum_ez; };
+struct BrickPlan { bool ok; size_t smem; int max_rows; };
 
 BrickPlan plan_bricks(const float *ys, int ny, const float *zs, int nk, const WnBands &b, int BY, int BZ, int BX = 32,
                       bool all_bands_resident = false)
 {
-    BrickPlan p{true, 0, 0, 0};
+    BrickPlan p{true, 0, 0};
     std::vector<int> my(ny), mz(nk);
     for (int band = 0; band < b.nbands; ++band) {
         for (int j = 0; j < ny; ++j) my[j] = first_cell(ys[j], b.scale[band]);
@@ -704,7 +529,6 @@ BrickPlan plan_bricks(const float *ys, int ny, const float *zs, int nk, const Wn
         for (int j0 = 0; j0 < ny; j0 += BY) ey = std::max<long long>(ey, (long long)my[std::min(j0 + BY, ny) - 1] - my[j0] + 3);
         for (int k0 = 0; k0 < nk; k0 += BZ) ez = std::max<long long>(ez, (long long)mz[std::min(k0 + BZ, nk) - 1] - mz[k0] + 3);
         if (ey * ez * BX > 1500 * 32) { p.ok = false; return p; }       // U must stay below ~192 KB
-        p.sum_ez += (int)ez;
         const int rows_b = (int)((ey * ez + 3) & ~3LL);
         p.max_rows = all_bands_resident ? p.max_rows + rows_b : std::max(p.max_rows, rows_b);
     }
@@ -739,28 +563,11 @@ int launch_brick4(WnTileView t, const float4 *tx, const float4 *ty, const float4
     return 1;
 }
 
-template <int BZ>
-int launch_plane4(WnTileView t, const float4 *tx, const float4 *ty, const float4 *tz, int nx, int ny, int nk, int nbands,
-                  float *out, const BrickPlan &plan, WnFold fold, cudaStream_t st)
-{
-    auto kern = t.pow2 ? k_mb3d_plane4<BZ, true> : k_mb3d_plane4<BZ, false>;
-    const int planes = plan.sum_ez;
-    const size_t smem = (size_t)planes * 8 * 32 * sizeof(float4) + (size_t)nbands * (128 + 8 + BZ) * sizeof(float4);
-    if (smem > 200 * 1024) return -1;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    dim3 grid((nx + 127) / 128, (ny + 7) / 8, (nk + BZ - 1) / BZ);
-    kern<<<grid, 256, smem, st>>>(t.Npad, t.n, tx, ty, tz, nx, ny, nk, nbands, planes, fold, out);
-    return 1;
-}
-
 // brick shapes (BY, BZ, threads); WN_BRICK=<index> overrides the default for tuning runs
 struct Shape { int by, bz, nt; };
 const Shape kShapes[] = { {16, 8, 256}, {16, 16, 256}, {8, 8, 256}, {8, 16, 256}, {8, 4, 256}, {16, 4, 256},
                           /* 6..9: four x-samples per thread (k_mb3d_brick4) */
-                          {8, 8, 256}, {16, 8, 256}, {8, 16, 256}, {8, 4, 256},
-                          /* 10, 11: per-plane XY pass (k_mb3d_plane4), 128 x 8 x 8 and 128 x 8 x 16 */
-                          {8, 8, 256}, {8, 16, 256} };
+                          {8, 8, 256}, {16, 8, 256}, {8, 16, 256}, {8, 4, 256} };
 const int kFirstShape4 = 6;
 const int kNumShapes = (int)(sizeof(kShapes) / sizeof(kShapes[0]));
 const int kDefaultShape = 5;
@@ -781,7 +588,7 @@ int brick_pass(WnTileView t, const float *dx, const float *dy, const float *dz, 
                int nx, int ny, int nk, const WnBands &b, WnFold fold, float *out, cudaStream_t st)
 {
     int pick = forced_shape();
-    BrickPlan plan{false, 0, 0, 0};
+    BrickPlan plan{false, 0, 0};
     // the float4 kernel needs 16-byte aligned rows of the output and of the period block
     const bool can4 = (nx % 4 == 0) && (!fold.P || fold.Lx % 4 == 0);
     if (pick >= kFirstShape4 && !can4) pick = -1;
@@ -829,8 +636,6 @@ int brick_pass(WnTileView t, const float *dx, const float *dy, const float *dz, 
         WN_BRICK4_CASE(6, 8, 8, 256)  WN_BRICK4_CASE(7, 16, 8, 256) WN_BRICK4_CASE(8, 8, 16, 256)
         WN_BRICK4_CASE(9, 8, 4, 256)
 #undef WN_BRICK4_CASE
-    case 10: r = launch_plane4<8>(t, tx, ty, tz, nx, ny, nk, b.nbands, out, plan, fold, st); break;
-    case 11: r = launch_plane4<16>(t, tx, ty, tz, nx, ny, nk, b.nbands, out, plan, fold, st); break;
     }
 #undef WN_BRICK_CASE
     cudaFreeAsync(tab, st);
