@@ -106,14 +106,54 @@ __device__ float eval3d_projected(const WnTileView &t, const float p[3], const f
     for (int i = 0; i < 3; ++i)
         if (hi[i] - lo[i] > 12 || hi[i] < lo[i] - 1 || hi[i] == 0x7fffffff) return 0.0f;
     const float q0 = FSUB(p[0], 1.5f), q1 = FSUB(p[1], 1.5f), q2 = FSUB(p[2], 1.5f);
+    // Row culling.  A candidate contributes only if every t_i lies in (0,3); in real arithmetic
+    //   t_i = 1.5 - D_i + n_i*dot/2,  D = p - c,  dot = n.D,
+    // which is affine in D_0 for a fixed (c1, c2) row, so the x range that can contribute is an interval.  It is
+    // evaluated in float with a slack `eps` that covers the reference's own rounding of t_i (it forms c_i + ... and
+    // p_i - 1.5 in float: a few ulp of |p_i|), so only candidates the reference rejects (weight 0) are skipped and
+    // the surviving ones are evaluated with the reference's exact operation order: the result stays bit-identical.
+    const float pmax = fmaxf(fmaxf(fabsf(p[0]), fabsf(p[1])), fabsf(p[2])) + 16.0f;
+    const float eps = pmax * 9.6e-7f + 1e-4f;                  // 8 ulp of the largest coordinate + a constant
+    const float b0 = 1.0f - 0.5f * nrm[0] * nrm[0];           // -d t_0 / d D_0  (in [0.5, 1])
+    const float b1 = 0.5f * nrm[0] * nrm[1];                   //  d t_1 / d D_0
+    const float b2 = 0.5f * nrm[0] * nrm[2];                   //  d t_2 / d D_0
     float result = 0.0f;
     for (int c2 = lo[2]; c2 <= hi[2]; ++c2) {
         const float f2 = (float)c2;
         const int i2 = tmod(c2, t) * t.n * t.n;
+        const float D2 = p[2] - f2;
         for (int c1 = lo[1]; c1 <= hi[1]; ++c1) {
             const float f1 = (float)c1;
             const int i1 = tmod(c1, t) * t.n;
-            for (int c0 = lo[0]; c0 <= hi[0]; ++c0) {
+            // admissible D_0 interval of this row
+            const float D1 = p[1] - f1;
+            const float K = nrm[1] * D1 + nrm[2] * D2;
+            float dlo = -1e30f, dhi = 1e30f;
+            {   // t_0 = (1.5 + n0 K/2) - b0 D0 in (-eps, 3+eps)
+                const float a = 1.5f + 0.5f * nrm[0] * K;
+                dlo = fmaxf(dlo, (a - 3.0f - eps) / b0);
+                dhi = fminf(dhi, (a + eps) / b0);
+            }
+            bool row_empty = false;
+            {   // t_1 = (1.5 - D1 + n1 K/2) + b1 D0
+                const float a = 1.5f - D1 + 0.5f * nrm[1] * K;
+                if (fabsf(b1) > 1e-6f) {
+                    const float x0 = (-eps - a) / b1, x1 = (3.0f + eps - a) / b1;
+                    dlo = fmaxf(dlo, fminf(x0, x1)); dhi = fminf(dhi, fmaxf(x0, x1));
+                } else if (a <= -eps - 8.0f * fabsf(b1) || a >= 3.0f + eps + 8.0f * fabsf(b1)) row_empty = true;
+            }
+            {   // t_2 = (1.5 - D2 + n2 K/2) + b2 D0
+                const float a = 1.5f - D2 + 0.5f * nrm[2] * K;
+                if (fabsf(b2) > 1e-6f) {
+                    const float x0 = (-eps - a) / b2, x1 = (3.0f + eps - a) / b2;
+                    dlo = fmaxf(dlo, fminf(x0, x1)); dhi = fminf(dhi, fmaxf(x0, x1));
+                } else if (a <= -eps - 8.0f * fabsf(b2) || a >= 3.0f + eps + 8.0f * fabsf(b2)) row_empty = true;
+            }
+            if (row_empty || !(dlo <= dhi)) continue;
+            // c0 = p0 - D0: widen by eps again for the float evaluation of the bounds themselves
+            const int r_lo = max(lo[0], (int)floorf(p[0] - dhi - eps));
+            const int r_hi = min(hi[0], (int)ceilf(p[0] - dlo + eps));
+            for (int c0 = r_lo; c0 <= r_hi; ++c0) {
                 const float f0 = (float)c0;
                 // dot = ((0 + n0 (p0-c0)) + n1 (p1-c1)) + n2 (p2-c2), cpp:239-240
                 float dot = FADD(0.0f, FMUL(nrm[0], FSUB(p[0], f0)));
@@ -138,7 +178,9 @@ __device__ float eval3d_projected(const WnTileView &t, const float p[3], const f
                     }
                     weight = FMUL(weight, piece);
                 }
-                if ((double)weight > 1e-6)                     // float vs double literal, cpp:257
+                // cpp:257 compares the float against the DOUBLE literal 1e-6.  float(1e-6) = 9.99999997e-7 is the
+                // largest float below that double, so `(double)w > 1e-6` <=> `w > 1e-6f` exactly (no FP64 needed).
+                if (weight > 1e-6f)
                     result = FADD(result, FMUL(weight, __ldg(t.N + tmod(c0, t) + i1 + i2)));
             }
         }
