@@ -94,6 +94,9 @@ int  wn_host_free(void *p);
 int  wn_rng_create(unsigned seed, wn_rng **out);
 int  wn_rng_destroy(wn_rng *rng);
 int  wn_rng_fill_gaussian(wn_rng *rng, float *out_host, size_t count);
+/* advance the engine by `raw_draws` 32-bit outputs and clear the distribution's cached variate: brings the host
+ * objects to the state they would have after a fill that wn_tile_build_seeded performed on the GPU */
+int  wn_rng_discard(wn_rng *rng, unsigned long long raw_draws);
 /* std::shuffle(iota(256), std::mt19937(seed)) duplicated to 512 ints: the constructors
  * PerlinNoise.hpp:29-34 and perlin.h:34-39 */
 int  wn_perlin_make_perm(unsigned seed, int32_t perm512_host[512]);
@@ -111,8 +114,10 @@ int  wn_tile_info(const wn_tile *tile, int *n, int *dims, size_t *count, int *bu
 int  wn_tile_build_from_gaussian(wn_tile *tile, const float *R, int space);
 /* device-side fill: MT19937 + libstdc++'s polar method + a restatement of glibc's logf, all on the GPU; same
  * accept/reject sequence and the same bits as `std::normal_distribution<float>` over a fresh
- * `std::mt19937(seed)` (i.e. a freshly constructed WaveletNoise), so the tile is bit-identical. */
-int  wn_tile_build_seeded(wn_tile *tile, unsigned seed);
+ * `std::mt19937(seed)` (i.e. a freshly constructed WaveletNoise), so the tile is bit-identical.
+ * *mt_draws (nullable) receives the number of raw engine outputs the fill consumed, so a host generator can be
+ * brought to the same state with wn_rng_discard / std::mt19937::discard. */
+int  wn_tile_build_seeded(wn_tile *tile, unsigned seed, unsigned long long *mt_draws);
 /* adopt finished coefficients (e.g. a copy of a WaveletNoise object, or a cached tile) */
 int  wn_tile_upload(wn_tile *tile, const float *N, int space);
 int  wn_tile_download(const wn_tile *tile, float *out, int space);

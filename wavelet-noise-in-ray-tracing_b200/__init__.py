@@ -172,10 +172,11 @@ class DataStats:
 class WaveletNoise:
     """Drop-in for the reference's class (WaveletNoise.h:20-59) with GPU-resident tile.
 
-    generateNoiseTile2D/3D fill the Gaussian field with the reference's generator sequence
-    (std::mt19937(seed) + std::normal_distribution<float>, state kept across calls like the reference's
-    members), run the filter passes on the GPU and keep the coefficients on the device; the host copy
-    returned by getNoiseCoefficients() is downloaded lazily.
+    generateNoiseTile2D/3D draw the Gaussian field from the reference's generator sequence
+    (std::mt19937(seed) + std::normal_distribution<float>) -- on the GPU for the first tile of an object
+    (wn_tile_build_seeded, bit-identical; the host generator is then advanced by the same number of raw draws),
+    from the host generator objects when the stream continues into a second tile -- run the filter passes on the GPU and keep the
+    coefficients on the device; the host copy returned by getNoiseCoefficients() is downloaded lazily.
     """
 
     def __init__(self, tileSize, seed=0, ctx=None, flags=WN_TILE_DEFAULT):
@@ -192,6 +193,7 @@ class WaveletNoise:
         self._tile = None
         self._dims = 0
         self._host = None
+        self._fresh = True              # the host generator has not been used yet (the first fill may run on the GPU)
 
     def __del__(self):
         try:
@@ -221,11 +223,21 @@ class WaveletNoise:
         """Next `count` variates of this object's generator (what the fill loops cpp:74-77/146-147 draw)."""
         R = np.empty(count, np.float32)
         check(lib.wn_rng_fill_gaussian(self._rng, C.c_void_p(R.ctypes.data), count))
+        self._fresh = False
         return R
 
     def _generate(self, dims, field=None):
         self._new_tile(dims)
         count = self.tileSizeN ** dims
+        if field is None and self._fresh:
+            # First tile of a fresh object: the whole fill runs on the GPU (wn_tile_build_seeded: MT19937 + polar
+            # method + logf on the device, bit-identical to the host objects); the host generator is then advanced
+            # by the same number of raw draws, so a later generate* continues the stream exactly like the reference.
+            draws = C.c_ulonglong(0)
+            check(lib.wn_tile_build_seeded(self._tile, self.randomSeed, C.byref(draws)))
+            check(lib.wn_rng_discard(self._rng, draws.value))
+            self._fresh = False
+            return
         if field is None:
             field = self.gaussian_field(count)
         ptr, space, keep = _in(field)
@@ -242,7 +254,7 @@ class WaveletNoise:
     def generate_seeded(self, dims, seed=None):
         """Build from a seed through wn_tile_build_seeded (fresh generator, like a new object)."""
         self._new_tile(dims)
-        check(lib.wn_tile_build_seeded(self._tile, self.randomSeed if seed is None else int(seed)))
+        check(lib.wn_tile_build_seeded(self._tile, self.randomSeed if seed is None else int(seed), None))
 
     def upload(self, coefficients, dims):
         """Adopt finished coefficients (n^dims floats)."""

@@ -46,13 +46,14 @@ SIGNATURES = {
     "wn_rng_create": (C.c_int, [C.c_uint, C.POINTER(vp)]),
     "wn_rng_destroy": (C.c_int, [vp]),
     "wn_rng_fill_gaussian": (C.c_int, [vp, vp, C.c_size_t]),
+    "wn_rng_discard": (C.c_int, [vp, C.c_ulonglong]),
     "wn_perlin_make_perm": (C.c_int, [C.c_uint, vp]),
     "wn_adjust_tile_size": (C.c_int, [C.c_int]),
     "wn_tile_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_uint, C.POINTER(vp)]),
     "wn_tile_destroy": (C.c_int, [vp]),
     "wn_tile_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     "wn_tile_build_from_gaussian": (C.c_int, [vp, vp, C.c_int]),
-    "wn_tile_build_seeded": (C.c_int, [vp, C.c_uint]),
+    "wn_tile_build_seeded": (C.c_int, [vp, C.c_uint, C.POINTER(C.c_ulonglong)]),
     "wn_tile_upload": (C.c_int, [vp, vp, C.c_int]),
     "wn_tile_download": (C.c_int, [vp, vp, C.c_int]),
     "wn_tile_device_ptr": (C.c_int, [vp, C.POINTER(vp)]),

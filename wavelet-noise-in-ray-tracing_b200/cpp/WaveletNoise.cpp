@@ -1,10 +1,11 @@
 // WaveletNoise.cpp -- GPU-backed implementation of the reference's `class WaveletNoise`.
 // Replaces reference WaveletNoise.cpp:20-291 behind the unchanged class declaration: every method forwards
 // to the C ABI of include/wn_b200.h (libwn_b200.so, hand-written sm_100a kernels).  No noise arithmetic runs
-// on the CPU here; the only host work is drawing the Gaussian field from the object's own
-// std::mt19937 / std::normal_distribution<float> members, which is what the reference's fill loops do
-// (WaveletNoise.cpp:74-77, :146-147) and what keeps the RNG stream semantics (a second generate* call
-// continues the stream).  Build this file WITHOUT -march/-ffast-math (or with -ffp-contract=off): libstdc++'s
+// on the CPU here.  The first tile of an object is filled on the GPU too (wn_tile_build_seeded, bit-identical to
+// the member generator objects, which are then advanced by the same number of raw draws with
+// std::mt19937::discard); when the object is asked for a second tile the reference continues the stream of its
+// std::mt19937 / std::normal_distribution<float> members (WaveletNoise.cpp:74-77, :146-147), and so does this
+// file: that tile's field is drawn from the members on the host.  Build this file WITHOUT -march/-ffast-math (or with -ffp-contract=off): libstdc++'s
 // polar method must not be FMA-contracted or the accept/reject sequence changes.
 #include "WaveletNoise.h"
 
@@ -24,6 +25,7 @@ struct DeviceTile {
     size_t count = 0;           // elements uploaded (to detect a stale entry after the vector changed)
     const float* host = nullptr;
 };
+
 
 std::mutex g_mu;
 std::unordered_map<const WaveletNoise*, DeviceTile> g_tiles;
@@ -104,16 +106,27 @@ WaveletNoise::~WaveletNoise()
     drop_locked(this);
 }
 
-static void generate_on_gpu(const WaveletNoise* self, int n, int dims, std::mt19937& rng,
+static void generate_on_gpu(const WaveletNoise* self, int n, int dims, unsigned seed, std::mt19937& rng,
                             std::normal_distribution<float>& gauss, std::vector<float>& coeff)
 {
     const size_t count = dims == 3 ? (size_t)n * n * n : (size_t)n * n;
-    std::vector<float> field(count);
-    for (size_t i = 0; i < count; ++i) field[i] = gauss(rng);          // memory order, like cpp:74-77 / :146-147
     wn_ctx* ctx = wnb::context();
     DeviceTile dt;
     wnb::check(wn_tile_create(ctx, n, dims, WN_TILE_DEFAULT, &dt.tile));
-    wnb::check(wn_tile_build_from_gaussian(dt.tile, field.data(), WN_HOST));
+    if (rng == std::mt19937(seed) && gauss == std::normal_distribution<float>(0.0f, 1.0f)) {
+        // The member generator is still in its freshly seeded state: run the fill itself on the GPU (MT19937 + polar
+        // method + logf on the device, bit-identical to `gauss(rng)`), then advance the members by the raw draws the
+        // fill consumed so that a later generate* call (or a copy of this object) continues the stream exactly
+        // like the reference (cpp:74-77 / :146-147 run on the same members).
+        unsigned long long draws = 0;
+        wnb::check(wn_tile_build_seeded(dt.tile, seed, &draws));
+        rng.discard(draws);
+        gauss.reset();                       // count is even (n is even), so no variate is left cached
+    } else {
+        std::vector<float> field(count);
+        for (size_t i = 0; i < count; ++i) field[i] = gauss(rng);          // memory order, like cpp:74-77 / :146-147
+        wnb::check(wn_tile_build_from_gaussian(dt.tile, field.data(), WN_HOST));
+    }
     coeff.resize(count);
     wnb::check(wn_tile_download(dt.tile, coeff.data(), WN_HOST));
     dt.dims = dims; dt.count = count; dt.host = coeff.data();
@@ -122,8 +135,8 @@ static void generate_on_gpu(const WaveletNoise* self, int n, int dims, std::mt19
     g_tiles[self] = dt;
 }
 
-void WaveletNoise::generateNoiseTile2D() { generate_on_gpu(this, tileSizeN, 2, rng, gaussianDist, noiseCoefficients); }
-void WaveletNoise::generateNoiseTile3D() { generate_on_gpu(this, tileSizeN, 3, rng, gaussianDist, noiseCoefficients); }
+void WaveletNoise::generateNoiseTile2D() { generate_on_gpu(this, tileSizeN, 2, randomSeed, rng, gaussianDist, noiseCoefficients); }
+void WaveletNoise::generateNoiseTile3D() { generate_on_gpu(this, tileSizeN, 3, randomSeed, rng, gaussianDist, noiseCoefficients); }
 
 float WaveletNoise::evaluate2D(const float p[2]) const
 {

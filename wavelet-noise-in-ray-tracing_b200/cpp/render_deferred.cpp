@@ -118,7 +118,7 @@ int main(int argc, char** argv)
         die(wn_ctx_create(g, &gpus[g].ctx));
         if (wavelet) {
             die(wn_tile_create(gpus[g].ctx, 128, 3, WN_TILE_DEFAULT, &gpus[g].tile));
-            die(wn_tile_build_seeded(gpus[g].tile, 12345));
+            die(wn_tile_build_seeded(gpus[g].tile, 12345, nullptr));
         } else {
             int32_t perm[512];
             die(wn_perlin_make_perm(5489u, perm));      // std::mt19937::default_seed

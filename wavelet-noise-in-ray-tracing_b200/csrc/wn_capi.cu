@@ -328,6 +328,13 @@ extern "C" int wn_rng_create(unsigned seed, wn_rng **out)
     return *out ? WN_OK : wn_fail(WN_ENOMEM, "out of host memory");
 }
 extern "C" int wn_rng_destroy(wn_rng *r) { delete r; return WN_OK; }
+extern "C" int wn_rng_discard(wn_rng *r, unsigned long long raw_draws)
+{
+    WN_REQUIRE(r, "wn_rng_discard: rng is NULL");
+    r->engine.discard(raw_draws);
+    r->gauss.reset();
+    return WN_OK;
+}
 extern "C" int wn_rng_fill_gaussian(wn_rng *r, float *out, size_t count)
 {
     WN_REQUIRE(r && (out || !count), "wn_rng_fill_gaussian: NULL argument");
@@ -488,7 +495,7 @@ extern "C" int wn_tile_build_from_gaussian(wn_tile *t, const float *R, int space
     return timing_end(c);
 }
 
-extern "C" int wn_tile_build_seeded(wn_tile *t, unsigned seed)
+extern "C" int wn_tile_build_seeded(wn_tile *t, unsigned seed, unsigned long long *mt_draws)
 {
     WN_REQUIRE(t, "wn_tile_build_seeded: tile is NULL");
     wn_ctx *c = t->ctx;
@@ -497,7 +504,7 @@ extern "C" int wn_tile_build_seeded(wn_tile *t, unsigned seed)
     float *dR = nullptr;
     unsigned long long *dacc = nullptr;
     WN_CUDA(cudaMallocAsync(&dR, t->count * sizeof(float), st));
-    WN_CUDA(cudaMallocAsync(&dacc, sizeof(unsigned long long), st));
+    WN_CUDA(cudaMallocAsync(&dacc, 2 * sizeof(unsigned long long), st));
     int rc = WN_OK;
     for (int margin = 20; ; margin *= 4) {                 // 2 % more attempts than expected; never short in practice
         timing_begin(c);
@@ -505,13 +512,14 @@ extern "C" int wn_tile_build_seeded(wn_tile *t, unsigned seed)
         const int nl = wn_launch_gaussian_fill(seed, dR, t->count, dacc, margin, st);
         if (nl < 0) { rc = wn_fail(WN_ECUDA, "device Gaussian fill failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         c->launches += (uint64_t)nl;
-        unsigned long long accepted = 0;
-        if (cudaMemcpyAsync(&accepted, dacc, sizeof(accepted), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        unsigned long long info[2] = { 0, 0 };
+        if (cudaMemcpyAsync(info, dacc, sizeof(info), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess) {
             rc = wn_fail(WN_ECUDA, "device Gaussian fill failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
-        if (2 * accepted >= t->count) {
+        if (2 * info[0] >= t->count) {
+            if (mt_draws) *mt_draws = 2 * (info[1] + 1);
             rc = tile_build_device(t, dR);
             timing_mark(c, st);
             break;

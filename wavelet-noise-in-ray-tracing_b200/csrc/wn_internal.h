@@ -93,8 +93,9 @@ int wn_launch_pad_tile(const float *N, float *Npad, int n, cudaStream_t st);
 
 // ---- device Gaussian fill (wn_rng.cu) ---------------------------------------------------------------
 // Fills out[0..count) with the libstdc++ normal_distribution<float>(mt19937(seed)) sequence, bit-identical to the
-// host objects.  *accepted (device, 8 bytes) receives the number of accepted polar attempts: the fill is complete
-// iff 2 * accepted >= count (check after synchronising; retry with a larger margin_permille otherwise).
+// host objects.  accepted (device, 16 bytes): [0] = accepted polar attempts -- the fill is complete iff
+// 2 * accepted >= count (check after synchronising; retry with a larger margin_permille otherwise); [1] = index of the
+// attempt that produced the last output (raw MT draws consumed = 2 * ([1] + 1)).
 // Scratch is stream-ordered (cudaMallocAsync).  Returns kernels launched, < 0 on error.
 int wn_launch_gaussian_fill(unsigned seed, float *out, size_t count, unsigned long long *accepted, int margin_permille,
                             cudaStream_t st);

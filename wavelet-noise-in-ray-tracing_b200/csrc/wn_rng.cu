@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(uint32_t *__restrict__ blo
 
 __global__ void __launch_bounds__(PB) k_polar_emit(const uint32_t *__restrict__ draws, size_t attempts,
                                                    const uint32_t *__restrict__ block_offset, float *__restrict__ out,
-                                                   size_t count)
+                                                   size_t count, unsigned long long *__restrict__ info)
 {
     __shared__ int warp_cnt[PB / 32];
     const size_t a = (size_t)blockIdx.x * PB + threadIdx.x;
@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(PB) k_polar_emit(const uint32_t *__restrict__ 
     for (int w = 0; w < warp; ++w) before += warp_cnt[w];
     const size_t slot = 2 * ((size_t)block_offset[blockIdx.x] + (size_t)before);
     if (slot >= count) return;
+    if (slot == ((count - 1) >> 1) * 2) info[1] = (unsigned long long)a;      // the attempt that produced the last output
     // mult = sqrt(-2*log(r2)/r2)
     const float mult = __fsqrt_rn(__fdiv_rn(__fmul_rn(-2.0f, glibc_logf(r2)), r2));
     out[slot] = __fadd_rn(__fmul_rn(__fmul_rn(y, mult), 1.0f), 0.0f);          // ret*stddev + mean
@@ -189,8 +190,9 @@ __global__ void __launch_bounds__(PB) k_polar_emit(const uint32_t *__restrict__ 
 
 } // namespace
 
-// Fills out[0..count).  `accepted` (device, 8 bytes) receives the number of accepted attempts so the caller can
-// verify 2*accepted >= count after synchronising.  margin_permille widens the number of attempts generated.
+// Fills out[0..count).  `accepted` (device, 2 x 8 bytes): [0] = number of accepted attempts (the fill is complete iff
+// 2*accepted >= count), [1] = index of the attempt that produced the last output, i.e. the generator has consumed
+// 2*([1]+1) raw draws.  margin_permille widens the number of attempts generated.
 int wn_launch_gaussian_fill(unsigned seed, float *out, size_t count, unsigned long long *accepted, int margin_permille,
                             cudaStream_t st)
 {
@@ -209,7 +211,7 @@ int wn_launch_gaussian_fill(unsigned seed, float *out, size_t count, unsigned lo
     k_mt19937<<<1, 256, 0, st>>>(seed, draws, (int)nblocks);
     k_polar_count<<<(unsigned)nb, PB, 0, st>>>(draws, attempts, bc);
     k_scan_blocks<<<1, 1024, 0, st>>>(bc, (int)nb, accepted);
-    k_polar_emit<<<(unsigned)nb, PB, 0, st>>>(draws, attempts, bc, out, count);
+    k_polar_emit<<<(unsigned)nb, PB, 0, st>>>(draws, attempts, bc, out, count, accepted);
     cudaFreeAsync(bc, st);
     cudaFreeAsync(draws, st);
     return 4;
