@@ -733,13 +733,13 @@ extern "C" int wn_multiband3d_lattice(const wn_tile *t, const float *xs, int nx,
     if (np < 0) return wn_fail(WN_ECUDA, "fast lattice prepare failed: %s", cudaGetErrorString(cudaGetLastError()));
     c->launches += (uint64_t)np;
     if (space == WN_DEVICE)
-        r = run_device(c, [&](cudaStream_t st) { return wn_mb3d_fast_run(tv, L, ys, zs, b, &plan, 0, nz, out, st); });
+        r = run_device(c, [&](cudaStream_t st) { return wn_mb3d_fast_run(tv, L, ys, zs, b, nullptr, &plan, 0, nz, out, st); });
     else {
         // HOST: chunk by whole z slices so each chunk is a lattice slab
         size_t slices_per_chunk = std::max<size_t>(1, kChunkSamples / slice);
         ChunkIO io; io.out = out; io.out_item = slice * sizeof(float);
         r = run_chunked_host(c, (size_t)nz, slices_per_chunk, io, [&](void *, void *, float *dout, size_t first, size_t cnt, cudaStream_t st) {
-            return wn_mb3d_fast_run(tv, L, ys, zs, b, &plan, (int)first, (int)cnt, dout, st);
+            return wn_mb3d_fast_run(tv, L, ys, zs, b, nullptr, &plan, (int)first, (int)cnt, dout, st);
         });
     }
     wn_mb3d_fast_finish(&plan, c->stream);

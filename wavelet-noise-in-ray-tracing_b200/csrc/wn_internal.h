@@ -79,13 +79,17 @@ int wn_launch_stats(const float *data, size_t count, double *partial, cudaStream
 // c holds DEVICE axis pointers; h_xs / h_ys / h_zs are the same axes on the host (brick planning, period detection).
 struct WnFastPlan {
     WnBands direct;             // bands evaluated per sample
+    unsigned char direct_rows[WN_MAX_BANDS];   // their rows in the call's axis tables (= original band indices)
     float *P;                   // sum of the folded bands on the period block Lx x Ly x Lz, or nullptr
     int Lx, Ly, Lz;
+    float4 *tab;                // axis tables of the whole call: [x | y | z] x tab_bands rows (see WnTabs)
+    int tab_bands, sx, sy, sz;
+    int owns_tab;               // the top-level plan frees the tables
 };
 int  wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const float *h_ys, const float *h_zs, WnBands b,
-                          WnFastPlan *plan, cudaStream_t st);
+                          WnFastPlan *plan, cudaStream_t st, int depth = 0);
 int  wn_mb3d_fast_run(WnTileView t, WnLattice c, const float *h_ys, const float *h_zs, const WnBands &all_bands,
-                      const WnFastPlan *plan, int k0, int nk, float *out, cudaStream_t st);
+                      const unsigned char *all_rows, const WnFastPlan *plan, int k0, int nk, float *out, cudaStream_t st);
 void wn_mb3d_fast_finish(WnFastPlan *plan, cudaStream_t st);
 
 // 3D tile -> x-padded replica (row pitch n+WN_TILE_PAD, the extra cells wrap around)

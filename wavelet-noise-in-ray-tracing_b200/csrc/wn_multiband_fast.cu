@@ -37,6 +37,18 @@ struct WnFold {
     int xmask, ymask;           // L-1 when L is a power of two, else -1 (use %)
 };
 
+// Axis tables of one top-level call: row r of x/y/z holds {w0, w1, w2, first tap cell} of every coordinate of the FULL
+// axis for original band r (k_axis_tables, one launch per call).  A kernel launch works on a subset of the bands
+// (row[]) and on a window of the lattice: the x/y windows always start at 0 (period blocks are prefixes of the
+// axes), the z window starts at kz0 (chunks of a WN_HOST call).
+struct WnTabs {
+    const float4 *x, *y, *z;
+    int sx, sy, sz;             // row strides = full axis lengths
+    int kz0;                    // first z entry of this launch
+    int nb;                     // bands of this launch
+    unsigned char row[WN_MAX_BANDS];
+};
+
 inline WnFold make_fold(const float *P, int Lx, int Ly, int Lz, int kphase)
 {
     WnFold f{P, Lx, Ly, Lz, kphase, -1, -1};
@@ -85,10 +97,10 @@ __global__ void k_axis_tables(WnLattice c, WnBands b, int k0, int nk, float4 *__
 
 template <int BY, int BZ, int NT, bool POW2>
 __global__ void __launch_bounds__(NT)
-k_mb3d_brick(const float *__restrict__ N, int n, const float4 *__restrict__ tabX,
-             const float4 *__restrict__ tabY, const float4 *__restrict__ tabZ, int nx, int ny, int nk, int nbands,
+k_mb3d_brick(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int nk,
              int max_rows, WnFold fold, float *__restrict__ out)
 {
+    const int nbands = tabs.nb;
     constexpr int NW = NT / 32;
     constexpr int C = BY / NW;                  // y columns per thread
     constexpr int PER_BAND = 32 + BY + BZ;      // table entries of one band this brick needs
@@ -112,9 +124,10 @@ k_mb3d_brick(const float *__restrict__ N, int n, const float4 *__restrict__ tabX
         for (int b = threadIdx.x >> 6; b < nbands; b += NT / 64) {
             if (q < PER_BAND) {
                 float4 v;
-                if (q < 32)           v = __ldg(tabX + b * nx + min(i0 + q, nx - 1));
-                else if (q < 32 + BY) v = __ldg(tabY + b * ny + min(j0 + q - 32, ny - 1));
-                else                  v = __ldg(tabZ + b * nk + min(k0 + q - 32 - BY, nk - 1));
+                const int row = tabs.row[b];
+                if (q < 32)           v = __ldg(tabs.x + row * tabs.sx + min(i0 + q, nx - 1));
+                else if (q < 32 + BY) v = __ldg(tabs.y + row * tabs.sy + min(j0 + q - 32, ny - 1));
+                else                  v = __ldg(tabs.z + row * tabs.sz + tabs.kz0 + min(k0 + q - 32 - BY, nk - 1));
                 smem4[max_rows * 8 + b * PER_BAND + q] = v;
             }
         }
@@ -259,10 +272,10 @@ k_mb3d_brick(const float *__restrict__ N, int n, const float4 *__restrict__ tabX
 // (bands with <= ~1 cell per sample); the per-sample arithmetic is identical to k_mb3d_brick.
 template <int BY, int BZ, int NT, bool POW2>
 __global__ void __launch_bounds__(NT)
-k_mb3d_brick4(const float *__restrict__ N, int n, const float4 *__restrict__ tabX,
-              const float4 *__restrict__ tabY, const float4 *__restrict__ tabZ, int nx, int ny, int nk, int nbands,
+k_mb3d_brick4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int nk,
               int max_rows, WnFold fold, float *__restrict__ out)
 {
+    const int nbands = tabs.nb;
     constexpr int NW = NT / 32;
     constexpr int C = BY / NW;
     constexpr int BX = 128;
@@ -282,9 +295,10 @@ k_mb3d_brick4(const float *__restrict__ N, int n, const float4 *__restrict__ tab
     for (int e = threadIdx.x; e < nbands * PER_BAND; e += NT) {
         const int b = e / PER_BAND, q = e - b * PER_BAND;
         float4 v;
-        if (q < BX)           v = __ldg(tabX + b * nx + min(i0 + q, nx - 1));
-        else if (q < BX + BY) v = __ldg(tabY + b * ny + min(j0 + q - BX, ny - 1));
-        else                  v = __ldg(tabZ + b * nk + min(k0 + q - BX - BY, nk - 1));
+        const int row = tabs.row[b];
+        if (q < BX)           v = __ldg(tabs.x + row * tabs.sx + min(i0 + q, nx - 1));
+        else if (q < BX + BY) v = __ldg(tabs.y + row * tabs.sy + min(j0 + q - BX, ny - 1));
+        else                  v = __ldg(tabs.z + row * tabs.sz + tabs.kz0 + min(k0 + q - BX - BY, nk - 1));
         // x entries are stored slot-major ([sample slot 0..3][lane]) so a lane's four LDS.128 are conflict-free
         s_tab[q < BX ? b * PER_BAND + (q & 3) * 32 + (q >> 2) : e] = v;
     }
@@ -473,17 +487,18 @@ __global__ void k_pad_tile(const float *__restrict__ N, float *__restrict__ P, i
 
 // fallback: one sample per thread, separable contraction, taps through the read-only path
 __global__ void __launch_bounds__(256)
-k_mb3d_gather(WnTileView t, const float4 *__restrict__ tabX, const float4 *__restrict__ tabY,
-              const float4 *__restrict__ tabZ, int nx, int ny, int nk, int nbands, float *__restrict__ out)
+k_mb3d_gather(WnTileView t, WnTabs tabs, int nx, int ny, int nk, float *__restrict__ out)
 {
+    const int nbands = tabs.nb;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y, k = blockIdx.z;
     if (i >= nx) return;
     const int n = t.n;
     float acc = 0.0f;
     for (int b = 0; b < nbands; ++b) {
-        const float4 ax = __ldg(tabX + (size_t)b * nx + i), ay = __ldg(tabY + (size_t)b * ny + j),
-                     az = __ldg(tabZ + (size_t)b * nk + k);
+        const int row = tabs.row[b];
+        const float4 ax = __ldg(tabs.x + row * tabs.sx + i), ay = __ldg(tabs.y + row * tabs.sy + j),
+                     az = __ldg(tabs.z + row * tabs.sz + tabs.kz0 + k);
         const float wx[3] = { ax.x, ax.y, ax.z }, wy[3] = { ay.x, ay.y, ay.z }, wz[3] = { az.x, az.y, az.z };
         int cx[3], cy[3], cz[3];
 #pragma unroll
@@ -538,7 +553,7 @@ BrickPlan plan_bricks(const float *ys, int ny, const float *zs, int nk, const Wn
 }
 
 template <int BY, int BZ, int NT>
-int launch_brick(WnTileView t, const float4 *tx, const float4 *ty, const float4 *tz, int nx, int ny, int nk, int nbands,
+int launch_brick(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
                  float *out, const BrickPlan &plan, WnFold fold, cudaStream_t st)
 {
     auto kern = t.pow2 ? k_mb3d_brick<BY, BZ, NT, true> : k_mb3d_brick<BY, BZ, NT, false>;
@@ -546,12 +561,12 @@ int launch_brick(WnTileView t, const float4 *tx, const float4 *ty, const float4 
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     dim3 grid((nx + 31) / 32, (ny + BY - 1) / BY, (nk + BZ - 1) / BZ);
-    kern<<<grid, NT, smem, st>>>(t.Npad, t.n, tx, ty, tz, nx, ny, nk, nbands, plan.max_rows, fold, out);
+    kern<<<grid, NT, smem, st>>>(t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, out);
     return 1;
 }
 
 template <int BY, int BZ, int NT>
-int launch_brick4(WnTileView t, const float4 *tx, const float4 *ty, const float4 *tz, int nx, int ny, int nk, int nbands,
+int launch_brick4(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
                   float *out, const BrickPlan &plan, WnFold fold, cudaStream_t st)
 {
     auto kern = t.pow2 ? k_mb3d_brick4<BY, BZ, NT, true> : k_mb3d_brick4<BY, BZ, NT, false>;
@@ -559,7 +574,7 @@ int launch_brick4(WnTileView t, const float4 *tx, const float4 *ty, const float4
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     dim3 grid((nx + 127) / 128, (ny + BY - 1) / BY, (nk + BZ - 1) / BZ);
-    kern<<<grid, NT, smem, st>>>(t.Npad, t.n, tx, ty, tz, nx, ny, nk, nbands, plan.max_rows, fold, out);
+    kern<<<grid, NT, smem, st>>>(t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, out);
     return 1;
 }
 
@@ -582,9 +597,9 @@ int forced_shape()
     return -1;
 }
 
-// One brick-kernel pass over the lattice (device axes dx/dy/dz, host copies hy/hz for planning): tables + kernel.
+// One brick-kernel pass over a lattice window (host copies hy/hz of the window's y/z axes for planning).
 // Returns kernels launched, or -1 when the lattice does not qualify (unsorted y/z, footprint too large, ...).
-int brick_pass(WnTileView t, const float *dx, const float *dy, const float *dz, const float *hy, const float *hz,
+int brick_pass(WnTileView t, const WnTabs &tabs, const float *hy, const float *hz,
                int nx, int ny, int nk, const WnBands &b, WnFold fold, float *out, cudaStream_t st)
 {
     int pick = forced_shape();
@@ -614,32 +629,20 @@ int brick_pass(WnTileView t, const float *dx, const float *dy, const float *dz, 
     const int BY = kShapes[pick].by, BZ = kShapes[pick].bz;
     const bool grid_ok = (ny + BY - 1) / BY <= 65535 && (nk + BZ - 1) / BZ <= 65535;
     if (!plan.ok || !grid_ok || plan.smem > 200 * 1024) return -1;
-    int launches = 0;
-    const size_t per_band = (size_t)nx + ny + nk;
-    float4 *tab = nullptr;
-    if (cudaMallocAsync(&tab, (per_band * b.nbands + 1) * sizeof(float4), st) != cudaSuccess) return -1;
-    float4 *tx = tab, *ty = tab + (size_t)b.nbands * nx, *tz = ty + (size_t)b.nbands * ny;
-    if (b.nbands > 0) {
-        const int total = (int)(per_band * b.nbands);
-        WnLattice c{dx, dy, dz, nx, ny, nk};
-        k_axis_tables<<<std::min((total + 255) / 256, 1184), 256, 0, st>>>(c, b, 0, nk, tx, ty, tz);
-        ++launches;
-    }
     int r = -1;
 #define WN_BRICK_CASE(idx, by, bz, nt) \
-    case idx: r = launch_brick<by, bz, nt>(t, tx, ty, tz, nx, ny, nk, b.nbands, out, plan, fold, st); break;
+    case idx: r = launch_brick<by, bz, nt>(t, tabs, nx, ny, nk, out, plan, fold, st); break;
     switch (pick) {
         WN_BRICK_CASE(0, 16, 8, 256)  WN_BRICK_CASE(1, 16, 16, 256) WN_BRICK_CASE(2, 8, 8, 256)
         WN_BRICK_CASE(3, 8, 16, 256)  WN_BRICK_CASE(4, 8, 4, 256)   WN_BRICK_CASE(5, 16, 4, 256)
 #define WN_BRICK4_CASE(idx, by, bz, nt) \
-    case idx: r = launch_brick4<by, bz, nt>(t, tx, ty, tz, nx, ny, nk, b.nbands, out, plan, fold, st); break;
+    case idx: r = launch_brick4<by, bz, nt>(t, tabs, nx, ny, nk, out, plan, fold, st); break;
         WN_BRICK4_CASE(6, 8, 8, 256)  WN_BRICK4_CASE(7, 16, 8, 256) WN_BRICK4_CASE(8, 8, 16, 256)
         WN_BRICK4_CASE(9, 8, 4, 256)
 #undef WN_BRICK4_CASE
     }
 #undef WN_BRICK_CASE
-    cudaFreeAsync(tab, st);
-    return r < 0 ? -1 : launches + r;
+    return r < 0 ? -1 : r;
 }
 
 // ---- periodic folding ---------------------------------------------------------------------------------------
@@ -706,19 +709,63 @@ int wn_launch_pad_tile(const float *N, float *Npad, int n, cudaStream_t st)
 // A fast-lattice call = prepare (fold decision on the WHOLE lattice + evaluation of the period block, once),
 // any number of z-slab launches (the chunks of a WN_HOST call), finish.  Deciding per call, not per slab, keeps
 // the result of a sample independent of how the call is chunked.
+namespace {
+
+WnTabs plan_tabs(const WnFastPlan *plan, const unsigned char *rows, int nb, int kz0)
+{
+    WnTabs tb;
+    tb.x = plan->tab; tb.y = tb.x + (size_t)plan->tab_bands * plan->sx; tb.z = tb.y + (size_t)plan->tab_bands * plan->sy;
+    tb.sx = plan->sx; tb.sy = plan->sy; tb.sz = plan->sz;
+    tb.kz0 = kz0; tb.nb = nb;
+    for (int i = 0; i < WN_MAX_BANDS; ++i) tb.row[i] = i < nb ? rows[i] : 0;
+    return tb;
+}
+
+}  // namespace
+
+// depth 0: `b` are the call's bands and the axis tables are computed here (one launch for every band and the full
+// axes); depth > 0 (period blocks): `plan` arrives with the parent's tables and rows[] = the original band indices of b.
 int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const float *h_ys, const float *h_zs, WnBands b,
-                         WnFastPlan *plan, cudaStream_t st)
+                         WnFastPlan *plan, cudaStream_t st, int depth)
 {
     plan->direct = b;
     plan->P = nullptr;
     plan->Lx = plan->Ly = plan->Lz = 1;
     const int nx = c.nx, ny = c.ny, nz = c.nz;
+    int launched = 0;
+    if (depth == 0) {
+        plan->tab = nullptr;
+        plan->owns_tab = 0;
+        plan->tab_bands = b.nbands; plan->sx = nx; plan->sy = ny; plan->sz = nz;
+        for (int i = 0; i < WN_MAX_BANDS; ++i) plan->direct_rows[i] = (unsigned char)i;
+        if (nx <= 0 || ny <= 0 || nz <= 0 || b.nbands <= 0) return 0;
+        const size_t per_band = (size_t)nx + ny + nz;
+        if (cudaMallocAsync(&plan->tab, per_band * b.nbands * sizeof(float4), st) != cudaSuccess) return -1;
+        plan->owns_tab = 1;
+        float4 *tx = plan->tab, *ty = tx + (size_t)b.nbands * nx, *tz = ty + (size_t)b.nbands * ny;
+        const int total_e = (int)(per_band * b.nbands);
+        k_axis_tables<<<std::min((total_e + 255) / 256, 1184), 256, 0, st>>>(c, b, 0, nz, tx, ty, tz);
+        launched = 1;
+    }
     if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
     const long long total = (long long)nx * ny * nz;
-    long long budget = 1LL << 22;                              // samples in the period block (16 MiB of floats)
+    long long budget = 1LL << 24;                              // samples in the period block: 64 MiB, L2 resident
     if (const char *e = getenv("WN_FOLD_BUDGET")) budget = atoll(e);
     struct Cand { int band; int px, py, pz; long long vol; };
     std::vector<Cand> cand;
+    // relative per-sample cost of evaluating a band directly, from its step in tile cells per sample (fitted to the
+    // measured single-band times: 1 : 1.1 : 1.3 : 2 : 5.4 for steps 1/8 .. 2)
+    double cost[WN_MAX_BANDS];
+    auto median_step = [](const float *a, int len, float scale) {
+        if (len < 2) return 0.0;
+        const int m = len / 2;
+        return std::fabs(((double)a[m] - (double)a[m - 1]) * (double)scale);
+    };
+    for (int i = 0; i < b.nbands; ++i) {
+        const double st = std::max(median_step(h_xs, nx, b.scale[i]),
+                                   std::max(median_step(h_ys, ny, b.scale[i]), median_step(h_zs, nz, b.scale[i])));
+        cost[i] = 1.0 + 1.2 * std::pow(st, 1.6);
+    }
     if (budget > 0)
         for (int i = 0; i < b.nbands; ++i) {
             Cand cd{i, axis_period(h_xs, nx, b.scale[i], t.n), axis_period(h_ys, ny, b.scale[i], t.n),
@@ -727,65 +774,92 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
             if (cd.vol * 4 <= total) cand.push_back(cd);
         }
     std::sort(cand.begin(), cand.end(), [](const Cand &a, const Cand &b2) { return a.vol < b2.vol; });
-    long long Lx = 1, Ly = 1, Lz = 1;
-    bool folded[WN_MAX_BANDS] = { false };
-    int nfold = 0;
+    // grow the folded set in order of period volume; keep the prefix with the lowest estimated cost
+    //   cost = sum_direct c_b * total + sum_folded c_b * block + 0.3 * total (the add) 
+    double direct_sum = 0.0;
+    for (int i = 0; i < b.nbands; ++i) direct_sum += cost[i];
+    double best = direct_sum * (double)total, folded_sum = 0.0;
+    long long Lx = 1, Ly = 1, Lz = 1, bLx = 1, bLy = 1, bLz = 1;
+    bool folded[WN_MAX_BANDS] = { false }, trial[WN_MAX_BANDS] = { false };
+    int nfold = 0, ntrial = 0;
     for (const Cand &cd : cand) {
         const long long lx = lcm_capped(Lx, cd.px, nx), ly = lcm_capped(Ly, cd.py, ny), lz = lcm_capped(Lz, cd.pz, nz);
         if (lx > nx || ly > ny || lz > nz) continue;
         if (lx * ly * lz > budget || lx * ly * lz * 4 > total) continue;
         Lx = lx; Ly = ly; Lz = lz;
-        folded[cd.band] = true;
-        ++nfold;
+        trial[cd.band] = true;
+        ++ntrial;
+        folded_sum += cost[cd.band];
+        direct_sum -= cost[cd.band];
+        const double est = direct_sum * (double)total + folded_sum * (double)(Lx * Ly * Lz) + 0.3 * (double)total;
+        if (est < best) {
+            best = est;
+            for (int i = 0; i < b.nbands; ++i) folded[i] = trial[i];
+            nfold = ntrial;
+            bLx = Lx; bLy = Ly; bLz = Lz;
+        }
     }
-    if (nfold == 0) return 0;
+    Lx = bLx; Ly = bLy; Lz = bLz;
+    if (nfold == 0) return launched;
     WnBands bf = b, bd = b;
     bf.nbands = bd.nbands = 0;
+    unsigned char rows_f[WN_MAX_BANDS] = { 0 }, rows_d[WN_MAX_BANDS] = { 0 };
     for (int i = 0; i < b.nbands; ++i) {
         WnBands &dst = folded[i] ? bf : bd;
+        (folded[i] ? rows_f : rows_d)[dst.nbands] = plan->direct_rows[i];
         dst.scale[dst.nbands] = b.scale[i];
         dst.weight[dst.nbands] = b.weight[i];
         ++dst.nbands;
     }
     float *P = nullptr;
     if (cudaMallocAsync(&P, (size_t)(Lx * Ly * Lz) * sizeof(float), st) != cudaSuccess) return -1;
-    const int r = brick_pass(t, c.xs, c.ys, c.zs, h_ys, h_zs, (int)Lx, (int)Ly, (int)Lz, bf, make_fold(nullptr, 1, 1, 1, 0), P, st);
-    if (r < 0) {                                               // period block does not qualify: evaluate everything directly
-        cudaFreeAsync(P, st);
-        return 0;
-    }
+    // The period block is itself a lattice, and the folded bands with the shortest periods repeat inside it: evaluate
+    // it with the same machinery (nested folding), e.g. bands 7, 8 of config 3 on 128^3 inside band 6's 256^3 block.
+    const WnLattice lc{c.xs, c.ys, c.zs, (int)Lx, (int)Ly, (int)Lz};
+    WnFastPlan inner = *plan;                                  // shares the parent's axis tables
+    inner.owns_tab = 0;
+    for (int i = 0; i < WN_MAX_BANDS; ++i) inner.direct_rows[i] = rows_f[i];
+    int max_depth = 3;
+    if (const char *e = getenv("WN_FOLD_NEST")) max_depth = atoi(e);
+    int r = depth < max_depth ? wn_mb3d_fast_prepare(t, lc, h_xs, h_ys, h_zs, bf, &inner, st, depth + 1) : 0;
+    if (r < 0) { cudaFreeAsync(P, st); return -1; }
+    if (depth >= max_depth) { inner.direct = bf; inner.P = nullptr; inner.Lx = inner.Ly = inner.Lz = 1; }
+    const int r2 = wn_mb3d_fast_run(t, lc, h_ys, h_zs, bf, rows_f, &inner, 0, (int)Lz, P, st);
+    wn_mb3d_fast_finish(&inner, st);
+    if (r2 < 0) { cudaFreeAsync(P, st); return -1; }
     plan->direct = bd;
+    for (int i = 0; i < WN_MAX_BANDS; ++i) plan->direct_rows[i] = rows_d[i];
     plan->P = P; plan->Lx = (int)Lx; plan->Ly = (int)Ly; plan->Lz = (int)Lz;
-    return r;
+    return launched + r + r2;
 }
 
 void wn_mb3d_fast_finish(WnFastPlan *plan, cudaStream_t st)
 {
     if (plan->P) cudaFreeAsync(plan->P, st);
     plan->P = nullptr;
+    if (plan->owns_tab && plan->tab) cudaFreeAsync(plan->tab, st);
+    plan->tab = nullptr;
+    plan->owns_tab = 0;
 }
 
+// all_bands / all_rows: every band of this (sub)lattice with its table row, used only by the generic fallback
 int wn_mb3d_fast_run(WnTileView t, WnLattice c, const float *h_ys, const float *h_zs, const WnBands &all_bands,
-                     const WnFastPlan *plan, int k0, int nk, float *out, cudaStream_t st)
+                     const unsigned char *all_rows, const WnFastPlan *plan, int k0, int nk, float *out, cudaStream_t st)
 {
     if (nk <= 0 || c.nx <= 0 || c.ny <= 0) return 0;
     const int nx = c.nx, ny = c.ny;
-    const float *dz = c.zs + k0, *hz = h_zs + k0;
+    const float *hz = h_zs + k0;
     const WnFold fold = make_fold(plan->P, plan->Lx, plan->Ly, plan->Lz, plan->P ? k0 % plan->Lz : 0);
-    const int r = brick_pass(t, c.xs, c.ys, dz, h_ys, hz, nx, ny, nk, plan->direct, fold, out, st);
+    const WnTabs tabs = plan_tabs(plan, plan->direct_rows, plan->direct.nbands, k0);
+    const int r = brick_pass(t, tabs, h_ys, hz, nx, ny, nk, plan->direct, fold, out, st);
     if (r >= 0) return r;
 
     // ---- generic path (unsorted y/z axes or huge steps): every band by direct gathers, no folding
     if (ny > 65535 || nk > 65535) return -1;                 // lattices that large are rejected
-    const WnBands &b = all_bands;
-    const size_t per_band = (size_t)nx + ny + nk;
-    float4 *tab = nullptr;
-    if (cudaMallocAsync(&tab, per_band * b.nbands * sizeof(float4), st) != cudaSuccess) return -1;
-    float4 *tx = tab, *ty = tab + (size_t)b.nbands * nx, *tz = ty + (size_t)b.nbands * ny;
-    const int total_e = (int)(per_band * b.nbands);
-    k_axis_tables<<<std::min((total_e + 255) / 256, 1184), 256, 0, st>>>(WnLattice{c.xs, c.ys, dz, nx, ny, nk}, b, 0, nk, tx, ty, tz);
+    unsigned char ident[WN_MAX_BANDS];
+    for (int i = 0; i < WN_MAX_BANDS; ++i) ident[i] = (unsigned char)i;
+    const WnTabs all = plan_tabs(plan, all_rows ? all_rows : ident, all_bands.nbands, k0);
     dim3 grid((nx + 255) / 256, ny, nk);
-    k_mb3d_gather<<<grid, 256, 0, st>>>(t, tx, ty, tz, nx, ny, nk, b.nbands, out);
-    cudaFreeAsync(tab, st);
-    return 2;
+    k_mb3d_gather<<<grid, 256, 0, st>>>(t, all, nx, ny, nk, out);
+    return 1;
 }
