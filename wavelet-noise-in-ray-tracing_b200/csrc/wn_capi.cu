@@ -66,6 +66,7 @@ struct wn_ctx {
     WnBuf in[2], aux[2], outb[2];
     cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
     WnBuf params;                        // coordinate axes etc. for the call in flight
+    std::vector<char> h_params;          // host staging of the same block
     WnBuf stats_partial;
     std::vector<cudaEvent_t> tev;        // timing event pool (pairs)
     size_t tev_used = 0;
@@ -121,6 +122,14 @@ extern "C" int wn_ctx_create(int device, wn_ctx **out)
     WN_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
     WN_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    {   // stream-ordered scratch (filter temporaries, axis tables, period blocks) is recycled, not returned to the OS
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     for (int i = 0; i < 2; ++i) {
         WN_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
         WN_CUDA(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
@@ -209,22 +218,35 @@ static int timing_end(wn_ctx *c)      // call after the streams have been synchr
     return WN_OK;
 }
 
-// copy a small host parameter array into the context's device parameter block (stream ordered)
+// Small host parameter arrays (coordinate axes, ...) of one call: packed into one host staging block and sent to the
+// context's device parameter block with a SINGLE stream-ordered copy (flush), instead of one copy per array.
 struct ParamWriter {
     wn_ctx *c;
     size_t off = 0;
     explicit ParamWriter(wn_ctx *ctx) : c(ctx) {}
-    int reserve(size_t bytes) { return buf_reserve(c->params, bytes + 1024); }
+    int reserve(size_t bytes)
+    {
+        int r = buf_reserve(c->params, bytes + 1024);
+        if (r) return r;
+        if (c->h_params.size() < bytes + 1024) c->h_params.resize(bytes + 1024);
+        return WN_OK;
+    }
     int put(const void *host, size_t bytes, const void **dptr)
     {
         off = (off + 255) & ~(size_t)255;
-        if (off + bytes > c->params.cap) return wn_fail(WN_EINVAL, "internal: parameter block overflow");
-        void *d = (char *)c->params.p + off;
-        // pageable source: the runtime stages it before returning, so the caller may reuse `host`
-        cudaError_t e = cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, c->stream);
-        if (e != cudaSuccess) return wn_fail(WN_ECUDA, "parameter upload failed: %s", cudaGetErrorString(e));
-        *dptr = d;
+        if (off + bytes > c->params.cap || off + bytes > c->h_params.size())
+            return wn_fail(WN_EINVAL, "internal: parameter block overflow");
+        std::memcpy(c->h_params.data() + off, host, bytes);
+        *dptr = (char *)c->params.p + off;
         off += bytes;
+        return WN_OK;
+    }
+    int flush()
+    {
+        if (!off) return WN_OK;
+        // pageable source: the runtime stages it before returning, so the staging block can be reused by the next call
+        cudaError_t e = cudaMemcpyAsync(c->params.p, c->h_params.data(), off, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) return wn_fail(WN_ECUDA, "parameter upload failed: %s", cudaGetErrorString(e));
         return WN_OK;
     }
 };
@@ -688,6 +710,7 @@ extern "C" int wn_eval2d_lattice(const wn_tile *t, const float *xs, int nx, cons
     WnLattice L{nullptr, nullptr, nullptr, nx, ny, 1};
     if ((r = pw.put(xs, nx * sizeof(float), (const void **)&L.xs))) return r;
     if ((r = pw.put(ys, ny * sizeof(float), (const void **)&L.ys))) return r;
+    if ((r = pw.flush())) return r;
     const WnTileView tv = tile_view(t);
     if (space == WN_DEVICE)
         return run_device(c, [&](cudaStream_t st) { return wn_launch_eval2d_lattice(tv, L, pre, 0, total, post, out, st); });
@@ -719,6 +742,7 @@ extern "C" int wn_multiband3d_lattice(const wn_tile *t, const float *xs, int nx,
     if ((r = pw.put(xs, nx * sizeof(float), (const void **)&L.xs))) return r;
     if ((r = pw.put(ys, ny * sizeof(float), (const void **)&L.ys))) return r;
     if ((r = pw.put(zs, nz * sizeof(float), (const void **)&L.zs))) return r;
+    if ((r = pw.flush())) return r;
     const WnTileView tv = tile_view(t);
     if (mode == WN_EVAL_EXACT) {
         if (space == WN_DEVICE)
@@ -757,7 +781,7 @@ static int make_affine(ParamWriter &pw, const float origin[3], const float e1[3]
     for (int i = 0; i < 3; ++i) { A->o[i] = origin[i]; A->e1[i] = e1[i]; A->e2[i] = e2[i]; }
     if ((r = pw.put(us, nu * sizeof(float), (const void **)&A->us))) return r;
     if ((r = pw.put(vs, nv * sizeof(float), (const void **)&A->vs))) return r;
-    return WN_OK;
+    return pw.flush();
 }
 
 extern "C" int wn_eval3d_projected_grid(const wn_tile *t, const float origin[3], const float e1[3], const float *us, int nu,
@@ -882,6 +906,7 @@ extern "C" int wn_perlin_lattice(const wn_perlin *pn, const float *xs, int nx, c
     if ((r = pw.put(xs, nx * sizeof(float), (const void **)&L.xs))) return r;
     if ((r = pw.put(ys, ny * sizeof(float), (const void **)&L.ys))) return r;
     if ((r = pw.put(zs, nz * sizeof(float), (const void **)&L.zs))) return r;
+    if ((r = pw.flush())) return r;
     const int32_t *perm = pn->d;
     if (space == WN_DEVICE)
         return run_device(c, [&](cudaStream_t st) { return wn_launch_perlin_lattice(perm, L, 0, total, out, st); });
