@@ -189,6 +189,9 @@ int  wn_perlin_grid(const wn_perlin *pn, const float origin[3],
  * returns in each colour channel for hit point p_i (xyz float, as stored in vec3). */
 int  wn_wavelet_texture_values(const wn_tile *tile3d, const float *p, size_t count,
                                double scale, int octave, float *grey, int space);
+/* the 2D branch of wavelet_texture::value (texture.h:86-99; use_3d = false): xy of p on a 2D tile */
+int  wn_wavelet_texture2d_values(const wn_tile *tile2d, const float *p, size_t count,
+                                 double scale, int octave, float *grey, int space);
 int  wn_perlin_texture_values(const wn_perlin *pn, const float *p, size_t count,
                               double scale, int octave, float *grey, int space);
 

@@ -116,6 +116,7 @@ double ref_perlin_noise(void *h, double x, double y, double z)
 
 #ifdef WNREF_WITH_TEXTURE
 void *ref_wavelet_texture_create(double scale, int octave) { return new wavelet_texture(scale, octave, true); }
+void *ref_wavelet_texture2d_create(double scale, int octave) { return new wavelet_texture(scale, octave, false); }
 void  ref_wavelet_texture_destroy(void *h) { delete static_cast<wavelet_texture *>(h); }
 void *ref_perlin_texture_create(double scale, int octave) { return new noise_texture(scale, octave); }
 void  ref_perlin_texture_destroy(void *h) { delete static_cast<noise_texture *>(h); }

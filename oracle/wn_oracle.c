@@ -613,6 +613,22 @@ double orc_wavelet_texture_value(const float *N, int n, const float p[3], double
     return 0.5 * (1.0 + c);
 }
 
+/* texture.h:86-99, the 2D branch (use_3d = false; never taken by the reference renderer): evaluate2D of the xy
+ * components, 1/sqrt(0.19686f), same clamp remap. */
+double orc_wavelet_texture2d_value(const float *N2, int n, const float p[3], double scale, int octave)
+{
+    float pos[2] = { (float)((double)p[0] * scale), (float)((double)p[1] * scale) };
+    const float octave_scale = (float)pow(2.0, (double)octave);
+    pos[0] *= octave_scale * 2.0f; pos[1] *= octave_scale * 2.0f;
+    double v = (double)orc_eval2d(N2, n, pos);
+    const float inv_stddev = 1.0f / sqrtf(0.19686f);
+    v *= (double)inv_stddev;
+    double c = v / 4.0;
+    if (c < -1.0) c = -1.0;
+    if (c > 1.0) c = 1.0;
+    return 0.5 * (1.0 + c);
+}
+
 /* texture.h:37-43: p * float(scale) * octave_scale in float (vec3 ops), Perlin in double. */
 double orc_perlin_texture_value(const int32_t perm[512], const float p[3], double scale, int octave)
 {

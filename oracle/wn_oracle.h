@@ -114,6 +114,8 @@ void   orc_perlin_lattice(const int32_t perm512[512], const float *xs, int nx,
 
 /* wavelet_texture::value, 3D branch: p (float xyz) -> grey in [0,1] (returned as double) */
 double orc_wavelet_texture_value(const float *N, int n, const float p[3], double scale, int octave);
+/* wavelet_texture::value, 2D branch (texture.h:86-99) */
+double orc_wavelet_texture2d_value(const float *N2, int n, const float p[3], double scale, int octave);
 /* noise_texture::value: Perlin grey */
 double orc_perlin_texture_value(const int32_t perm512[512], const float p[3], double scale, int octave);
 

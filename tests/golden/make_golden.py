@@ -84,6 +84,8 @@ def main():
     out["tex_pts"] = tp
     out["tex_wavelet_s1_o4"] = ref.texture_values("wavelet", 1.0, 4, tp)
     out["tex_wavelet_s0.37_o3"] = ref.texture_values("wavelet", 0.37, 3, tp)
+    out["tex_wavelet2d_s1_o4"] = ref.texture_values("wavelet2d", 1.0, 4, tp)
+    out["tex_wavelet2d_s0.37_o3"] = ref.texture_values("wavelet2d", 0.37, 3, tp)
     out["tex_perlin_s1_o4"] = ref.texture_values("perlin", 1.0, 4, tp)
     out["tex_perlin_s0.37_o5"] = ref.texture_values("perlin", 0.37, 5, tp)
     np.savez_compressed(os.path.join(HERE, "ref_vectors.npz"), **out)

@@ -57,6 +57,8 @@ class Oracle:
         L.orc_perlin_noise.argtypes = [i32p, C.c_double, C.c_double, C.c_double]
         L.orc_wavelet_texture_value.restype = C.c_double
         L.orc_wavelet_texture_value.argtypes = [f32p, C.c_int, f32p, C.c_double, C.c_int]
+        L.orc_wavelet_texture2d_value.restype = C.c_double
+        L.orc_wavelet_texture2d_value.argtypes = [f32p, C.c_int, f32p, C.c_double, C.c_int]
         L.orc_perlin_texture_value.restype = C.c_double
         L.orc_perlin_texture_value.argtypes = [i32p, f32p, C.c_double, C.c_int]
         L.orc_fnv1a64.restype = C.c_uint64
@@ -215,6 +217,10 @@ class Oracle:
         p = _f32(p)
         return self.L.orc_wavelet_texture_value(_fp(N), n, _fp(p), scale, octave)
 
+    def wavelet_texture2d_value(self, N2, n, p, scale, octave):
+        p = _f32(p)
+        return self.L.orc_wavelet_texture2d_value(_fp(N2), n, _fp(p), scale, octave)
+
     def perlin_texture_value(self, perm, p, scale, octave):
         p = _f32(p)
         return self.L.orc_perlin_texture_value(perm.ctypes.data_as(i32p), _fp(p), scale, octave)
@@ -272,6 +278,9 @@ class RefLib:
         if self.has_texture:
             L.ref_wavelet_texture_create.restype = C.c_void_p
             L.ref_wavelet_texture_create.argtypes = [C.c_double, C.c_int]
+            if hasattr(L, 'ref_wavelet_texture2d_create'):
+                L.ref_wavelet_texture2d_create.restype = C.c_void_p
+                L.ref_wavelet_texture2d_create.argtypes = [C.c_double, C.c_int]
             L.ref_perlin_texture_create.restype = C.c_void_p
             L.ref_perlin_texture_create.argtypes = [C.c_double, C.c_int]
             L.ref_wavelet_texture_destroy.argtypes = [C.c_void_p]
@@ -347,7 +356,11 @@ class RefLib:
     def texture_values(self, kind, scale, octave, pts, threads=1):
         pts = _f32(pts)
         out = np.empty(pts.size // 3, np.float32)
-        if kind == "wavelet":
+        if kind == "wavelet2d":
+            h = self.L.ref_wavelet_texture2d_create(scale, octave)
+            self.L.ref_texture_values(h, _fp(pts), out.size, _fp(out), threads)
+            self.L.ref_wavelet_texture_destroy(h)
+        elif kind == "wavelet":
             h = self.L.ref_wavelet_texture_create(scale, octave)
             self.L.ref_texture_values(h, _fp(pts), out.size, _fp(out), threads)
             self.L.ref_wavelet_texture_destroy(h)

@@ -189,6 +189,8 @@ def test_texture_hooks(wn, ref_vectors):
     assert wt.value(0, 0, tp[0])[0] == rv["tex_wavelet_s1_o4"][0]
     wt2 = wn.wavelet_texture(0.37, 3, True)
     assert_bits(wt2.values(tp), rv["tex_wavelet_s0.37_o3"], "wavelet_texture s.37 o3")
+    assert_bits(wn.wavelet_texture(1.0, 4, False).values(tp), rv["tex_wavelet2d_s1_o4"], "wavelet_texture 2D s1 o4")
+    assert_bits(wn.wavelet_texture(0.37, 3, False).values(tp), rv["tex_wavelet2d_s0.37_o3"], "wavelet_texture 2D s.37 o3")
     assert_bits(wn.noise_texture(1.0, 4).values(tp), rv["tex_perlin_s1_o4"], "noise_texture s1 o4")
     assert_bits(wn.noise_texture(0.37, 5).values(tp), rv["tex_perlin_s0.37_o5"], "noise_texture s.37 o5")
 

@@ -426,6 +426,20 @@ class WaveletNoise:
         return out
 
 
+def _texture2d_values(self, pts, scale, octave, out=None):
+    """grey value of wavelet_texture::value's 2D branch for each hit point (texture.h:86-99)."""
+    self._need()
+    ptr, space, keep = _in(pts)
+    count = (keep.numel() if _is_torch(keep) else keep.size) // 3
+    optr, out = _out(out, (count,), space, keep if _is_torch(keep) else None)
+    check(lib.wn_wavelet_texture2d_values(self._tile, C.c_void_p(ptr), count, float(scale), int(octave),
+                                          C.c_void_p(optr), space))
+    return out
+
+
+WaveletNoise.texture2d_values = _texture2d_values
+
+
 class PerlinNoise:
     """Drop-in for PerlinNoise (experient/PerlinNoise.hpp:9-61) == perlin (perlin.h:14-91)."""
 
@@ -524,14 +538,5 @@ class wavelet_texture:
     def values(self, pts, out=None):
         if self.use_3d_noise and self.noise_3d is not None:
             return self.noise_3d.texture_values(pts, self.scale, self.octave_level, out)
-        # 2D branch (texture.h:86-99), unused by the renderer: composed from the 2D evaluator on the host side
-        pts = np.asarray(pts, np.float32).reshape(-1, 3)
-        pos = (pts[:, :2].astype(np.float64) * self.scale).astype(np.float32)
-        oct2 = np.float32(2.0 ** self.octave_level) * np.float32(2.0)
-        v = self.noise_2d.evaluate2D_points(pos, float(oct2), 1.0).astype(np.float64)
-        v *= np.float64(np.float32(1.0) / np.sqrt(np.float32(0.19686)))
-        g = (0.5 * (1.0 + np.clip(v / 4.0, -1.0, 1.0))).astype(np.float32)
-        if out is not None:
-            out[...] = g
-            return out
-        return g
+        # 2D branch (texture.h:86-99), never taken by the reference renderer
+        return self.noise_2d.texture2d_values(pts, self.scale, self.octave_level, out)

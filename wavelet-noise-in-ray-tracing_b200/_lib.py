@@ -74,6 +74,7 @@ SIGNATURES = {
     "wn_perlin_lattice": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int]),
     "wn_perlin_grid": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, vp, C.c_int]),
     "wn_wavelet_texture_values": (C.c_int, [vp, vp, C.c_size_t, C.c_double, C.c_int, vp, C.c_int]),
+    "wn_wavelet_texture2d_values": (C.c_int, [vp, vp, C.c_size_t, C.c_double, C.c_int, vp, C.c_int]),
     "wn_perlin_texture_values": (C.c_int, [vp, vp, C.c_size_t, C.c_double, C.c_int, vp, C.c_int]),
     "wn_stats_compute": (C.c_int, [vp, vp, C.c_size_t, C.c_int, C.POINTER(WnStats)]),
 }

@@ -964,6 +964,27 @@ extern "C" int wn_wavelet_texture_values(const wn_tile *t, const float *p, size_
     });
 }
 
+extern "C" int wn_wavelet_texture2d_values(const wn_tile *t, const float *p, size_t count, double scale, int octave,
+                                           float *grey, int space)
+{
+    WN_NEED_TILE(t, 2, "wn_wavelet_texture2d_values");
+    WN_NEED_SPACE(space);
+    if (!count) return WN_OK;
+    WN_REQUIRE(p && grey, "wn_wavelet_texture2d_values: NULL buffer");
+    wn_ctx *c = t->ctx;
+    DeviceGuard g(c->device);
+    const float octave_scale = (float)std::pow(2.0, (double)octave);       // texture.h:91
+    const float oct2 = octave_scale * 2.0f;
+    const float inv_std = 1.0f / std::sqrt(0.19686f);                      // texture.h:97
+    const WnTileView tv = tile_view(t);
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_wavelet_texture2d(tv, p, count, scale, oct2, inv_std, grey, st); });
+    ChunkIO io; io.in = p; io.in_item = 3 * sizeof(float); io.out = grey;
+    return run_chunked_host(c, count, kChunkSamples, io, [&](void *din, void *, float *dout, size_t, size_t cnt, cudaStream_t st) {
+        return wn_launch_wavelet_texture2d(tv, (const float *)din, cnt, scale, oct2, inv_std, dout, st);
+    });
+}
+
 extern "C" int wn_perlin_texture_values(const wn_perlin *pn, const float *p, size_t count, double scale, int octave,
                                         float *grey, int space)
 {

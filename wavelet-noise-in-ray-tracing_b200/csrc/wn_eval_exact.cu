@@ -308,6 +308,19 @@ __global__ void k_wavelet_texture(WnTileView t, const float *p, size_t count, do
     c = (c < -1.0) ? -1.0 : ((1.0 < c) ? 1.0 : c);                 // std::clamp
     grey[s] = __double2float_rn(__dmul_rn(0.5, __dadd_rn(1.0, c)));
 }
+// texture.h:86-99 (2D branch): evaluate2D of the xy components; inv_std = 1.0f/sqrt(0.19686f)
+__global__ void k_wavelet_texture2d(WnTileView t, const float *p, size_t count, double scale, float oct2, float inv_std,
+                                    float *grey)
+{
+    WN_TID_OR_RETURN(count);
+    const float qx = FMUL(__double2float_rn(__dmul_rn((double)__ldg(p + 3 * s), scale)), oct2);
+    const float qy = FMUL(__double2float_rn(__dmul_rn((double)__ldg(p + 3 * s + 1), scale)), oct2);
+    double v = (double)eval2d(t, qx, qy);
+    v = __dmul_rn(v, (double)inv_std);
+    double c = __ddiv_rn(v, 4.0);
+    c = (c < -1.0) ? -1.0 : ((1.0 < c) ? 1.0 : c);
+    grey[s] = __double2float_rn(__dmul_rn(0.5, __dadd_rn(1.0, c)));
+}
 // texture.h:37-43: (p * float(scale)) * octave_scale in float, Perlin in double, 0.5*(1+v)
 __global__ void k_perlin_texture(const int32_t *perm, const float *p, size_t count, float scale_f, float oct, float *grey)
 {
@@ -429,6 +442,13 @@ int wn_launch_wavelet_texture(WnTileView t, const float *p, size_t count, double
 {
     if (!count) return 0;
     k_wavelet_texture<<<blocks_for(count, WN_T), WN_T, 0, st>>>(t, p, count, scale, oct2, inv_std, grey);
+    return 1;
+}
+int wn_launch_wavelet_texture2d(WnTileView t, const float *p, size_t count, double scale, float oct2, float inv_std,
+                                float *grey, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_wavelet_texture2d<<<blocks_for(count, WN_T), WN_T, 0, st>>>(t, p, count, scale, oct2, inv_std, grey);
     return 1;
 }
 int wn_launch_perlin_texture(const int32_t *perm, const float *p, size_t count, float scale_f, float oct,

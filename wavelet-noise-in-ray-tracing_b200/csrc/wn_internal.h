@@ -66,6 +66,8 @@ int wn_launch_perlin_affine(const int32_t *perm, WnAffine c, size_t first, size_
 // texture hooks: scale (double) and octave as in texture.h
 int wn_launch_wavelet_texture(WnTileView t, const float *p, size_t count, double scale, float oct2, float inv_std,
                               float *grey, cudaStream_t st);
+int wn_launch_wavelet_texture2d(WnTileView t, const float *p, size_t count, double scale, float oct2, float inv_std,
+                                float *grey, cudaStream_t st);
 int wn_launch_perlin_texture(const int32_t *perm, const float *p, size_t count, float scale_f, float oct,
                              float *grey, cudaStream_t st);
 // stats: partial[] must hold 4*WN_STATS_BLOCKS doubles; result read back by the host
