@@ -91,6 +91,35 @@ def generatePerlinNoise3DSliced(imageSize, octave, outputFile, perlin):
     return image
 
 
+def raw_to_json_dict(image):
+    """The JSON the reference's viewer loads (threejs/convert_raw_to_json.py:12-90): width, height,
+    original_range{min,max,mean,std} (float64 statistics of the float32 image) and the data normalised to [0,1]."""
+    a = np.asarray(image, dtype=np.float32).astype(np.float64)
+    size = int(np.sqrt(a.size))
+    a = a.reshape(size, size)
+    lo, hi = float(np.min(a)), float(np.max(a))
+    norm = (a - lo) / (hi - lo) if hi != lo else np.zeros_like(a)
+    return {"width": size, "height": size,
+            "original_range": {"min": lo, "max": hi, "mean": float(np.mean(a)), "std": float(np.std(a))},
+            "data": norm.flatten().tolist()}
+
+
+JSON_NAMES = {"wavelet_noise_2D_octave_": "wavelet_noise_2d_octave", "wavelet_noise_3Dsliced_octave_": "wavelet_noise_3d_sliced_octave",
+              "wavelet_noise_3Dprojected_octave_": "wavelet_noise_3d_projected_octave",
+              "perlin_noise_2D_octave_": "perlin_noise_2d_octave", "perlin_noise_3Dsliced_octave_": "perlin_noise_3d_sliced_octave"}
+
+
+def export_json(images, json_dir):
+    """Write the 15 viewer files (threejs/result_json/*.json naming, convert_raw_to_json.py:92-157)."""
+    import json
+    os.makedirs(json_dir, exist_ok=True)
+    for name, image in images.items():
+        for prefix, out_prefix in JSON_NAMES.items():
+            if name.startswith(prefix):
+                with open(os.path.join(json_dir, out_prefix + name[len(prefix):] + ".json"), "w") as f:
+                    json.dump(raw_to_json_dict(image), f, separators=(",", ":"))
+
+
 def main(out_dir="result_raw", ctx=None):
     """experient/main.cpp:131-168"""
     print("=== Wavelet & Perlin Noise Comparison Generation ===")
