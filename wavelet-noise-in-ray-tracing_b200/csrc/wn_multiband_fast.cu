@@ -46,8 +46,10 @@ struct WnTabs {
     int sx, sy, sz;             // row strides = full axis lengths
     int kz0;                    // first z entry of this launch
     int nb;                     // bands of this launch
-    unsigned char row[WN_MAX_BANDS];
+    unsigned long long rowbits;  // table row of band b in bits [4b, 4b+4): no indexed kernel parameter, no local copy
 };
+static_assert(WN_MAX_BANDS <= 16, "rows are packed four bits each");
+__host__ __device__ __forceinline__ int tabs_row(const WnTabs &t, int b) { return (int)((t.rowbits >> (4 * b)) & 15ull); }
 
 inline WnFold make_fold(const float *P, int Lx, int Ly, int Lz, int kphase)
 {
@@ -124,7 +126,7 @@ k_mb3d_brick(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, in
         for (int b = threadIdx.x >> 6; b < nbands; b += NT / 64) {
             if (q < PER_BAND) {
                 float4 v;
-                const int row = tabs.row[b];
+                const int row = tabs_row(tabs, b);
                 if (q < 32)           v = __ldg(tabs.x + row * tabs.sx + min(i0 + q, nx - 1));
                 else if (q < 32 + BY) v = __ldg(tabs.y + row * tabs.sy + min(j0 + q - 32, ny - 1));
                 else                  v = __ldg(tabs.z + row * tabs.sz + tabs.kz0 + min(k0 + q - 32 - BY, nk - 1));
@@ -265,13 +267,148 @@ k_mb3d_brick(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, in
     }
 }
 
+// ---- pieces shared by the float4 kernels (k_mb3d_brick4, k_mb3d_col4): a CTA owns 128 x BY x BZ samples, lane l owns
+// x = 4l..4l+3.  Shared memory (float4 units): U[max_rows][32] | tables nbands x (128 + BY + BZ) | rowoff[max_rows] (int)
+struct Q4Foot { int ey[WN_MAX_BANDS], ez[WN_MAX_BANDS], row0[WN_MAX_BANDS + 1]; };
+
+// axis-table entries of every band for this brick; ends with a barrier
+template <int BY, int BZ, int NT>
+__device__ __forceinline__ void q4_load_tables(float4 *s_tab, const WnTabs &tabs, int i0, int j0, int k0,
+                                               int nx, int ny, int nk)
+{
+    constexpr int BX = 128, PER_BAND = BX + BY + BZ;
+    for (int e = threadIdx.x; e < tabs.nb * PER_BAND; e += NT) {
+        const int b = e / PER_BAND, q = e - b * PER_BAND;
+        float4 v;
+        const int row = tabs_row(tabs, b);
+        if (q < BX)           v = __ldg(tabs.x + row * tabs.sx + min(i0 + q, nx - 1));
+        else if (q < BX + BY) v = __ldg(tabs.y + row * tabs.sy + min(j0 + q - BX, ny - 1));
+        else                  v = __ldg(tabs.z + row * tabs.sz + tabs.kz0 + min(k0 + q - BX - BY, nk - 1));
+        // x entries are stored slot-major ([sample slot 0..3][lane]) so a lane's four LDS.128 are conflict-free
+        s_tab[q < BX ? b * PER_BAND + (q & 3) * 32 + (q >> 2) : e] = v;
+    }
+    __syncthreads();
+}
+
+// footprints of all bands (Ey, Ez, first U row: U holds every band at once) and the tile-row offset of every U row;
+// ends with a barrier
+template <int BY, int BZ, int NT, bool POW2>
+__device__ __forceinline__ void q4_footprints(const float4 *s_tab, int nbands, int n, Q4Foot &ft, int *s_rowoff)
+{
+    constexpr int BX = 128, PER_BAND = BX + BY + BZ, pow2 = POW2 ? 1 : 0;
+    const int pitch = n + WN_TILE_PAD;
+    if (threadIdx.x == 0) {
+        int row0 = 0;
+        for (int b = 0; b < nbands; ++b) {
+            const float4 *tY = s_tab + b * PER_BAND + BX, *tZ = tY + BY;
+            // clamped entries repeat the last valid one, so the last entry carries the brick's last tap cell
+            const int ey = __float_as_int(tY[BY - 1].w) - __float_as_int(tY[0].w) + 3;
+            const int ez = __float_as_int(tZ[BZ - 1].w) - __float_as_int(tZ[0].w) + 3;
+            ft.ey[b] = ey; ft.ez[b] = ez; ft.row0[b] = row0;
+            row0 += (ey * ez + 1) & ~1;                      // each band starts on an even row
+        }
+        ft.row0[nbands] = row0;
+    }
+    __syncthreads();
+    for (int b = 0; b < nbands; ++b) {
+        const float4 *tY = s_tab + b * PER_BAND + BX, *tZ = tY + BY;
+        const int my0 = __float_as_int(tY[0].w), mz0 = __float_as_int(tZ[0].w);
+        const int Ey = ft.ey[b], rows = Ey * ft.ez[b], rows2 = (rows + 1) & ~1, row0 = ft.row0[b];
+        const float inv_ey = 1.0f / (float)Ey;
+        for (int r = threadIdx.x; r < rows2; r += NT) {
+            const int rr = min(r, rows - 1);
+            const int cz = (int)(((float)rr + 0.5f) * inv_ey), cy = rr - cz * Ey;       // exact for rows < 2^20
+            s_rowoff[row0 + r] = (tmodf(mz0 + cz, n, pow2) * n + tmodf(my0 + cy, n, pow2)) * pitch;
+        }
+    }
+    __syncthreads();
+}
+
+// X pass of one band: U[row][4 lanes-samples] = sum_f wx[f] * N[row][cx + f] for rows [row0, row1)
+template <int NT, bool POW2>
+__device__ __forceinline__ void q4_xpass(const float *__restrict__ N, int n, const float4 *tX, float4 *U4,
+                                         const int *s_rowoff, int row0, int row1)
+{
+    constexpr int NW = NT / 32, pow2 = POW2 ? 1 : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4 t0 = tX[lane], t1 = tX[32 + lane], t2 = tX[64 + lane], t3 = tX[96 + lane];
+    const int c0 = __float_as_int(t0.w), c1 = __float_as_int(t1.w), c2 = __float_as_int(t2.w), c3 = __float_as_int(t3.w);
+    const int cmin = min(min(c0, c1), min(c2, c3)), cmax = max(max(c0, c1), max(c2, c3));
+    // Bands with <= 1/2 cell per sample: a lane's four samples touch at most the four cells cmin..cmin+3, so
+    // four loads serve all of them.  Each sample's three weights are placed on that 4-cell footprint (the
+    // unused slot is an exact 0, fmaf(0, a, x) == x), which keeps the result bit-identical to the 12-load form.
+    const bool narrow = __all_sync(0xffffffffu, cmax - cmin <= 1);
+    if (narrow) {
+        const float *base = N + tmodf(cmin, n, pow2);     // padded rows hold cells 0..n+2, so cmin+3 stays in the row
+        const bool s0 = c0 != cmin, s1 = c1 != cmin, s2 = c2 != cmin, s3 = c3 != cmin;
+        // W[e][0..3]: shifted by one slot when the sample's first cell is cmin + 1
+        const float a00 = s0 ? 0.0f : t0.x, a01 = s0 ? t0.x : t0.y, a02 = s0 ? t0.y : t0.z, a03 = s0 ? t0.z : 0.0f;
+        const float a10 = s1 ? 0.0f : t1.x, a11 = s1 ? t1.x : t1.y, a12 = s1 ? t1.y : t1.z, a13 = s1 ? t1.z : 0.0f;
+        const float a20 = s2 ? 0.0f : t2.x, a21 = s2 ? t2.x : t2.y, a22 = s2 ? t2.y : t2.z, a23 = s2 ? t2.z : 0.0f;
+        const float a30 = s3 ? 0.0f : t3.x, a31 = s3 ? t3.x : t3.y, a32 = s3 ? t3.y : t3.z, a33 = s3 ? t3.z : 0.0f;
+        for (int r = row0 + warp * 2; r < row1; r += NW * 2) {
+            const int2 o = *reinterpret_cast<const int2 *>(s_rowoff + r);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float *q = base + (unsigned)(h ? o.y : o.x);
+                const float v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
+                float4 u;
+                u.x = fmaf(a03, v3, fmaf(a02, v2, fmaf(a01, v1, a00 * v0)));
+                u.y = fmaf(a13, v3, fmaf(a12, v2, fmaf(a11, v1, a10 * v0)));
+                u.z = fmaf(a23, v3, fmaf(a22, v2, fmaf(a21, v1, a20 * v0)));
+                u.w = fmaf(a33, v3, fmaf(a32, v2, fmaf(a31, v1, a30 * v0)));
+                U4[(r + h) * 32 + lane] = u;
+            }
+        }
+    } else {
+        const float *b0 = N + tmodf(c0, n, pow2), *b1 = N + tmodf(c1, n, pow2);
+        const float *b2 = N + tmodf(c2, n, pow2), *b3 = N + tmodf(c3, n, pow2);
+        for (int r = row0 + warp * 2; r < row1; r += NW * 2) {
+            const int2 o = *reinterpret_cast<const int2 *>(s_rowoff + r);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const unsigned off = (unsigned)(h ? o.y : o.x);
+                const float *q0 = b0 + off, *q1 = b1 + off, *q2 = b2 + off, *q3 = b3 + off;
+                float4 u;
+                u.x = fmaf(t0.z, __ldg(q0 + 2), fmaf(t0.y, __ldg(q0 + 1), t0.x * __ldg(q0)));
+                u.y = fmaf(t1.z, __ldg(q1 + 2), fmaf(t1.y, __ldg(q1 + 1), t1.x * __ldg(q1)));
+                u.z = fmaf(t2.z, __ldg(q2 + 2), fmaf(t2.y, __ldg(q2 + 1), t2.x * __ldg(q2)));
+                u.w = fmaf(t3.z, __ldg(q3 + 2), fmaf(t3.y, __ldg(q3 + 1), t3.x * __ldg(q3)));
+                U4[(r + h) * 32 + lane] = u;
+            }
+        }
+    }
+}
+
+// y contraction of one tile-z plane for a lane's four samples: V = sum_f wy[f] * U[cz][cy + f]
+__device__ __forceinline__ float4 q4_ycontract(const float4 *uu, const float4 ty)
+{
+    const float4 u0 = uu[0], u1 = uu[32], u2 = uu[64];
+    float4 nv;
+    nv.x = fmaf(ty.z, u2.x, fmaf(ty.y, u1.x, ty.x * u0.x));
+    nv.y = fmaf(ty.z, u2.y, fmaf(ty.y, u1.y, ty.x * u0.y));
+    nv.z = fmaf(ty.z, u2.z, fmaf(ty.y, u1.z, ty.x * u0.z));
+    nv.w = fmaf(ty.z, u2.w, fmaf(ty.y, u1.w, ty.x * u0.w));
+    return nv;
+}
+
+// a += sum_f wz[f] * v[f], in the order every multiband kernel of this file uses
+__device__ __forceinline__ float4 q4_zcontract(float4 a, const float4 tz, const float4 (&v)[3])
+{
+    a.x = fmaf(tz.x, v[0].x, fmaf(tz.y, v[1].x, fmaf(tz.z, v[2].x, a.x)));
+    a.y = fmaf(tz.x, v[0].y, fmaf(tz.y, v[1].y, fmaf(tz.z, v[2].y, a.y)));
+    a.z = fmaf(tz.x, v[0].z, fmaf(tz.y, v[1].z, fmaf(tz.z, v[2].z, a.z)));
+    a.w = fmaf(tz.x, v[0].w, fmaf(tz.y, v[1].w, fmaf(tz.z, v[2].w, a.w)));
+    return a;
+}
+
 // ---- k_mb3d_brick4: same algorithm, four x-samples per thread --------------------------------------------------
 // A CTA owns 128 x BY x BZ samples; lane l owns x = 4l..4l+3, so U rows, the y-contracted window, the accumulators,
 // the period-block loads and the output stores are all float4 (LDS.128 / LDG.128 / STG.128): the per-sample FMA
 // count is unchanged but every other instruction is amortised over four samples.  Used for small footprints
 // (bands with <= ~1 cell per sample); the per-sample arithmetic is identical to k_mb3d_brick.
 template <int BY, int BZ, int NT, bool POW2>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, BY * BZ <= 64 ? 3 : 1)
 k_mb3d_brick4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int nk,
               int max_rows, WnFold fold, float *__restrict__ out)
 {
@@ -280,7 +417,6 @@ k_mb3d_brick4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, i
     constexpr int C = BY / NW;
     constexpr int BX = 128;
     constexpr int PER_BAND = BX + BY + BZ;
-    constexpr int pow2 = POW2 ? 1 : 0;
     static_assert(BY % NW == 0, "BY must be a multiple of the warp count");
     // dynamic shared memory (float4 units): U[max_rows][32] | tables nbands x PER_BAND | rowoff[max_rows] (int)
     extern __shared__ float4 smem4[];
@@ -290,99 +426,14 @@ k_mb3d_brick4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, i
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY, k0 = blockIdx.z * BZ;
-    const int pitch = n + WN_TILE_PAD;
 
-    for (int e = threadIdx.x; e < nbands * PER_BAND; e += NT) {
-        const int b = e / PER_BAND, q = e - b * PER_BAND;
-        float4 v;
-        const int row = tabs.row[b];
-        if (q < BX)           v = __ldg(tabs.x + row * tabs.sx + min(i0 + q, nx - 1));
-        else if (q < BX + BY) v = __ldg(tabs.y + row * tabs.sy + min(j0 + q - BX, ny - 1));
-        else                  v = __ldg(tabs.z + row * tabs.sz + tabs.kz0 + min(k0 + q - BX - BY, nk - 1));
-        // x entries are stored slot-major ([sample slot 0..3][lane]) so a lane's four LDS.128 are conflict-free
-        s_tab[q < BX ? b * PER_BAND + (q & 3) * 32 + (q >> 2) : e] = v;
-    }
-    __syncthreads();
+    q4_load_tables<BY, BZ, NT>(s_tab, tabs, i0, j0, k0, nx, ny, nk);
+    __shared__ Q4Foot ft;
+    q4_footprints<BY, BZ, NT, POW2>(s_tab, nbands, n, ft, s_rowoff);
 
-    // ---- footprints of all bands: Ey, Ez and the first U row of each band (U holds every band at once)
-    __shared__ int s_ey[WN_MAX_BANDS], s_ez[WN_MAX_BANDS], s_row0[WN_MAX_BANDS + 1];
-    if (threadIdx.x == 0) {
-        int row0 = 0;
-        for (int b = 0; b < nbands; ++b) {
-            const float4 *tY = s_tab + b * PER_BAND + BX, *tZ = tY + BY;
-            const int ey = __float_as_int(tY[BY - 1].w) - __float_as_int(tY[0].w) + 3;
-            const int ez = __float_as_int(tZ[BZ - 1].w) - __float_as_int(tZ[0].w) + 3;
-            s_ey[b] = ey; s_ez[b] = ez; s_row0[b] = row0;
-            row0 += (ey * ez + 1) & ~1;                      // each band starts on an even row
-        }
-        s_row0[nbands] = row0;
-    }
-    __syncthreads();
-    for (int b = 0; b < nbands; ++b) {
-        const float4 *tY = s_tab + b * PER_BAND + BX, *tZ = tY + BY;
-        const int my0 = __float_as_int(tY[0].w), mz0 = __float_as_int(tZ[0].w);
-        const int Ey = s_ey[b], rows = Ey * s_ez[b], rows2 = (rows + 1) & ~1, row0 = s_row0[b];
-        const float inv_ey = 1.0f / (float)Ey;
-        for (int r = threadIdx.x; r < rows2; r += NT) {
-            const int rr = min(r, rows - 1);
-            const int cz = (int)(((float)rr + 0.5f) * inv_ey), cy = rr - cz * Ey;       // exact for rows < 2^20
-            s_rowoff[row0 + r] = (tmodf(mz0 + cz, n, pow2) * n + tmodf(my0 + cy, n, pow2)) * pitch;
-        }
-    }
-    __syncthreads();
-
-    // ---- X pass for every band: U[row][4 lanes-samples] = sum_f wx[f] * N[row][cx + f]
-    for (int b = 0; b < nbands; ++b) {
-        const float4 *tX = s_tab + b * PER_BAND;
-        const int row0 = s_row0[b], row1 = s_row0[b + 1];
-        const float4 t0 = tX[lane], t1 = tX[32 + lane], t2 = tX[64 + lane], t3 = tX[96 + lane];
-        const int c0 = __float_as_int(t0.w), c1 = __float_as_int(t1.w), c2 = __float_as_int(t2.w), c3 = __float_as_int(t3.w);
-        const int cmin = min(min(c0, c1), min(c2, c3)), cmax = max(max(c0, c1), max(c2, c3));
-        // Bands with <= 1/2 cell per sample: a lane's four samples touch at most the four cells cmin..cmin+3, so
-        // four loads serve all of them.  Each sample's three weights are placed on that 4-cell footprint (the
-        // unused slot is an exact 0, fmaf(0, a, x) == x), which keeps the result bit-identical to the 12-load form.
-        const bool narrow = __all_sync(0xffffffffu, cmax - cmin <= 1);
-        if (narrow) {
-            const float *base = N + tmodf(cmin, n, pow2);     // padded rows hold cells 0..n+2, so cmin+3 stays in the row
-            const bool s0 = c0 != cmin, s1 = c1 != cmin, s2 = c2 != cmin, s3 = c3 != cmin;
-            // W[e][0..3]: shifted by one slot when the sample's first cell is cmin + 1
-            const float a00 = s0 ? 0.0f : t0.x, a01 = s0 ? t0.x : t0.y, a02 = s0 ? t0.y : t0.z, a03 = s0 ? t0.z : 0.0f;
-            const float a10 = s1 ? 0.0f : t1.x, a11 = s1 ? t1.x : t1.y, a12 = s1 ? t1.y : t1.z, a13 = s1 ? t1.z : 0.0f;
-            const float a20 = s2 ? 0.0f : t2.x, a21 = s2 ? t2.x : t2.y, a22 = s2 ? t2.y : t2.z, a23 = s2 ? t2.z : 0.0f;
-            const float a30 = s3 ? 0.0f : t3.x, a31 = s3 ? t3.x : t3.y, a32 = s3 ? t3.y : t3.z, a33 = s3 ? t3.z : 0.0f;
-            for (int r = row0 + warp * 2; r < row1; r += NW * 2) {
-                const int2 o = *reinterpret_cast<const int2 *>(s_rowoff + r);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const float *q = base + (unsigned)(h ? o.y : o.x);
-                    const float v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
-                    float4 u;
-                    u.x = fmaf(a03, v3, fmaf(a02, v2, fmaf(a01, v1, a00 * v0)));
-                    u.y = fmaf(a13, v3, fmaf(a12, v2, fmaf(a11, v1, a10 * v0)));
-                    u.z = fmaf(a23, v3, fmaf(a22, v2, fmaf(a21, v1, a20 * v0)));
-                    u.w = fmaf(a33, v3, fmaf(a32, v2, fmaf(a31, v1, a30 * v0)));
-                    U4[(r + h) * 32 + lane] = u;
-                }
-            }
-        } else {
-            const float *b0 = N + tmodf(c0, n, pow2), *b1 = N + tmodf(c1, n, pow2);
-            const float *b2 = N + tmodf(c2, n, pow2), *b3 = N + tmodf(c3, n, pow2);
-            for (int r = row0 + warp * 2; r < row1; r += NW * 2) {
-                const int2 o = *reinterpret_cast<const int2 *>(s_rowoff + r);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const unsigned off = (unsigned)(h ? o.y : o.x);
-                    const float *q0 = b0 + off, *q1 = b1 + off, *q2 = b2 + off, *q3 = b3 + off;
-                    float4 u;
-                    u.x = fmaf(t0.z, __ldg(q0 + 2), fmaf(t0.y, __ldg(q0 + 1), t0.x * __ldg(q0)));
-                    u.y = fmaf(t1.z, __ldg(q1 + 2), fmaf(t1.y, __ldg(q1 + 1), t1.x * __ldg(q1)));
-                    u.z = fmaf(t2.z, __ldg(q2 + 2), fmaf(t2.y, __ldg(q2 + 1), t2.x * __ldg(q2)));
-                    u.w = fmaf(t3.z, __ldg(q3 + 2), fmaf(t3.y, __ldg(q3 + 1), t3.x * __ldg(q3)));
-                    U4[(r + h) * 32 + lane] = u;
-                }
-            }
-        }
-    }
+    // ---- X pass for every band
+    for (int b = 0; b < nbands; ++b)
+        q4_xpass<NT, POW2>(N, n, s_tab + b * PER_BAND, U4, s_rowoff, ft.row0[b], ft.row0[b + 1]);
     __syncthreads();
 
     // ---- YZ pass for every band
@@ -395,14 +446,14 @@ k_mb3d_brick4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, i
     for (int b = 0; b < nbands; ++b) {
         const float4 *tY = s_tab + b * PER_BAND + BX, *tZ = tY + BY;
         const int my0 = __float_as_int(tY[0].w), mz0 = __float_as_int(tZ[0].w);
-        const int slab4 = s_ey[b] * 32;                         // one cz plane of this band's U in float4 units
+        const int slab4 = ft.ey[b] * 32;                         // one cz plane of this band's U in float4 units
         float4 ty[C];
         const float4 *ucol[C];
         float4 v[C][3];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             ty[c] = tY[warp + c * NW];
-            ucol[c] = U4 + s_row0[b] * 32 + (__float_as_int(ty[c].w) - my0) * 32 + lane + 2 * slab4;
+            ucol[c] = U4 + ft.row0[b] * 32 + (__float_as_int(ty[c].w) - my0) * 32 + lane + 2 * slab4;
             v[c][0] = v[c][1] = v[c][2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
         int base = -3;
@@ -414,24 +465,13 @@ k_mb3d_brick4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, i
                 ++base;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const float4 *uu = ucol[c] + base * slab4;
-                    const float4 u0 = uu[0], u1 = uu[32], u2 = uu[64];
-                    float4 nv;
-                    nv.x = fmaf(ty[c].z, u2.x, fmaf(ty[c].y, u1.x, ty[c].x * u0.x));
-                    nv.y = fmaf(ty[c].z, u2.y, fmaf(ty[c].y, u1.y, ty[c].x * u0.y));
-                    nv.z = fmaf(ty[c].z, u2.z, fmaf(ty[c].y, u1.z, ty[c].x * u0.z));
-                    nv.w = fmaf(ty[c].z, u2.w, fmaf(ty[c].y, u1.w, ty[c].x * u0.w));
+                    const float4 nv = q4_ycontract(ucol[c] + base * slab4, ty[c]);
                     v[c][0] = v[c][1]; v[c][1] = v[c][2]; v[c][2] = nv;
                 }
             }
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                float4 a = acc[c][k];
-                a.x = fmaf(tz.x, v[c][0].x, fmaf(tz.y, v[c][1].x, fmaf(tz.z, v[c][2].x, a.x)));
-                a.y = fmaf(tz.x, v[c][0].y, fmaf(tz.y, v[c][1].y, fmaf(tz.z, v[c][2].y, a.y)));
-                a.z = fmaf(tz.x, v[c][0].z, fmaf(tz.y, v[c][1].z, fmaf(tz.z, v[c][2].z, a.z)));
-                a.w = fmaf(tz.x, v[c][0].w, fmaf(tz.y, v[c][1].w, fmaf(tz.z, v[c][2].w, a.w)));
-                acc[c][k] = a;
+                acc[c][k] = q4_zcontract(acc[c][k], tz, v[c]);
             }
         }
     }
@@ -473,6 +513,139 @@ k_mb3d_brick4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, i
     }
 }
 
+// ---- k_mb3d_col4: one or two direct bands, streaming along z -----------------------------------------------------
+// Same tables, X pass and per-sample arithmetic as k_mb3d_brick4, but the band loop is inside the z loop: each band
+// keeps only its 3-deep y-contracted window in registers and every sample is finished (period-block value added,
+// stored) as soon as it is computed.  Without BZ accumulators per thread the brick can be long in z (BZ = 32), which
+// amortises the tables, the footprint set-up and the X pass over four times as many samples and leaves registers for
+// five CTAs per SM.  This is the main kernel whenever folding leaves at most two bands to evaluate per sample.
+//
+// Block order: when the period block divides the lattice, the (y, z) bricks are enumerated replica-first
+// (blockIdx.y = ((y brick in period) * yrep + y replica) * zrep + z replica, blockIdx.z = z brick in period), so the
+// CTAs that add the same period-block lines run back to back and the block is read from HBM once even when it is
+// much larger than L2.
+struct WnOrder { int yrep, yper, zrep, zper; };          // replicas and bricks per period; {1, nyb, 1, nzb} = plain order
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory"); }
+
+template <int NB, int BY, int BZ, int NT, int RING, bool POW2>
+__global__ void __launch_bounds__(NT, NB == 1 ? 4 : 3)
+k_mb3d_col4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int nk,
+            int max_rows, WnFold fold, WnOrder ord, float *__restrict__ out)
+{
+    constexpr int BX = 128;
+    constexpr int PER_BAND = BX + BY + BZ;
+    static_assert(BY == NT / 32, "one y row per warp");
+    extern __shared__ float4 smem4[];
+    float4 *U4 = smem4;
+    float4 *s_tab = smem4 + max_rows * 32;
+    int *s_rowoff = reinterpret_cast<int *>(s_tab + NB * PER_BAND);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int yb, zb;
+    {
+        const int gy = blockIdx.y, rz = gy % ord.zrep, t = gy / ord.zrep;
+        yb = t / ord.yrep + (t % ord.yrep) * ord.yper;
+        zb = rz * ord.zper + blockIdx.z;
+    }
+    const int i0 = blockIdx.x * BX, j0 = yb * BY, k0 = zb * BZ;
+    const int i = i0 + 4 * lane, j = j0 + warp;
+    const bool active = i < nx && j < ny;
+    const int kmax = min(BZ, nk - k0);
+
+    // Period-block column of this thread (host guarantees nx % 4 == 0 and Lx % 4 == 0).  Its values travel through a
+    // per-thread ring of RING float4 slots in shared memory filled by cp.async: the first RING-1 planes are requested
+    // here, before the tables and the X pass, and plane k+RING-1 is requested when plane k is consumed, so the loads
+    // have the whole prologue and RING-1 z steps to land and cost no registers.
+    float4 *ring = reinterpret_cast<float4 *>(s_rowoff + max_rows) + threadIdx.x;
+    const size_t pplane = (size_t)fold.Lx * fold.Ly;
+    const float *pcol = nullptr, *pp = nullptr;
+    int kk = 0;
+    const bool folded = fold.P != nullptr;
+    if (folded && active) {
+        const unsigned pi = (unsigned)(fold.xmask >= 0 ? (i & fold.xmask) : i % fold.Lx);
+        const unsigned pj = (unsigned)(fold.ymask >= 0 ? (j & fold.ymask) : j % fold.Ly);
+        pcol = fold.P + (pi + pj * (unsigned)fold.Lx);
+        kk = fold.kphase + k0;
+        if (kk >= fold.Lz) kk %= fold.Lz;
+        pp = pcol + kk * pplane;
+#pragma unroll
+        for (int d = 0; d < RING - 1; ++d) {
+            if (d < kmax) {
+                cp_async16(ring + d * NT, pp);
+                if (++kk == fold.Lz) { kk = 0; pp = pcol; } else pp += pplane;
+            }
+            cp_async_commit();
+        }
+    }
+
+    q4_load_tables<BY, BZ, NT>(s_tab, tabs, i0, j0, k0, nx, ny, nk);
+    __shared__ Q4Foot ft;
+    q4_footprints<BY, BZ, NT, POW2>(s_tab, NB, n, ft, s_rowoff);
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+        q4_xpass<NT, POW2>(N, n, s_tab + b * PER_BAND, U4, s_rowoff, ft.row0[b], ft.row0[b + 1]);
+    __syncthreads();
+    if (!active) return;                                       // no barrier below
+
+    // per band: y weights, the 3-deep window of y-contracted tile-z planes (starts at the brick's first tap plane) and
+    // the next plane to contract
+    float4 ty[NB], v[NB][3];
+    const float4 *unext[NB], *tZ[NB];
+    int slab4[NB], mz0[NB], base[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const float4 *tY = s_tab + b * PER_BAND + BX;
+        tZ[b] = tY + BY;
+        ty[b] = tY[warp];
+        slab4[b] = ft.ey[b] * 32;
+        mz0[b] = __float_as_int(tZ[b][0].w);
+        const float4 *u = U4 + ft.row0[b] * 32 + (__float_as_int(ty[b].w) - __float_as_int(tY[0].w)) * 32 + lane;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) v[b][f] = q4_ycontract(u + f * slab4[b], ty[b]);
+        unext[b] = u + 3 * slab4[b];
+        base[b] = 0;
+    }
+
+    const size_t plane = (size_t)nx * ny;
+    float *o = out + ((size_t)i + (size_t)nx * j + plane * k0);
+#pragma unroll 4
+    for (int k = 0; k < kmax; ++k) {
+        float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const float4 tz = tZ[b][k];
+            const int rel = __float_as_int(tz.w) - mz0[b];
+#pragma unroll 1
+            while (base[b] < rel) {
+                ++base[b];
+                const float4 nv = q4_ycontract(unext[b], ty[b]);
+                unext[b] += slab4[b];
+                v[b][0] = v[b][1]; v[b][1] = v[b][2]; v[b][2] = nv;
+            }
+            a = q4_zcontract(a, tz, v[b]);
+        }
+        if (folded) {
+            if (k + RING - 1 < kmax) {                         // slot of plane k-1, consumed in the previous step
+                cp_async16(ring + ((k + RING - 1) % RING) * NT, pp);
+                if (++kk == fold.Lz) { kk = 0; pp = pcol; } else pp += pplane;
+            }
+            cp_async_commit();
+            cp_async_wait<RING - 1>();                         // plane k has landed
+            const float4 pv = ring[(k % RING) * NT];
+            a.x += pv.x; a.y += pv.y; a.z += pv.z; a.w += pv.w;
+        }
+        __stcs(reinterpret_cast<float4 *>(o), a);
+        o += plane;
+    }
+}
+
 __global__ void k_pad_tile(const float *__restrict__ N, float *__restrict__ P, int n)
 {
     const int pitch = n + WN_TILE_PAD;
@@ -496,7 +669,7 @@ k_mb3d_gather(WnTileView t, WnTabs tabs, int nx, int ny, int nk, float *__restri
     const int n = t.n;
     float acc = 0.0f;
     for (int b = 0; b < nbands; ++b) {
-        const int row = tabs.row[b];
+        const int row = tabs_row(tabs, b);
         const float4 ax = __ldg(tabs.x + row * tabs.sx + i), ay = __ldg(tabs.y + row * tabs.sy + j),
                      az = __ldg(tabs.z + row * tabs.sz + tabs.kz0 + k);
         const float wx[3] = { ax.x, ax.y, ax.z }, wy[3] = { ay.x, ay.y, ay.z }, wz[3] = { az.x, az.y, az.z };
@@ -578,6 +751,32 @@ int launch_brick4(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
     return 1;
 }
 
+template <int NB, int RING>
+int launch_col4(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
+                float *out, const BrickPlan &plan, WnFold fold, cudaStream_t st)
+{
+    constexpr int BY = 8, BZ = 32, NT = 256;
+    auto kern = t.pow2 ? k_mb3d_col4<NB, BY, BZ, NT, RING, true> : k_mb3d_col4<NB, BY, BZ, NT, RING, false>;
+    const size_t smem = plan.smem + (fold.P ? (size_t)RING * NT * sizeof(float4) : 0);   // + the period-block ring
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    const int nyb = (ny + BY - 1) / BY, nzb = (nk + BZ - 1) / BZ;
+    WnOrder ord{1, nyb, 1, nzb};
+    // replica-first order when the period block cannot stay in L2 by itself (config 3, 512 MiB block: 1.08 vs 1.17 ms
+    // per 1024^3); WN_REPLICA_ORDER=0/1 forces it for A/B runs
+    bool replica = fold.P && (long long)fold.Lx * fold.Ly * fold.Lz > (8LL << 20);
+    if (const char *e = getenv("WN_REPLICA_ORDER")) replica = fold.P && atoi(e) != 0;
+    if (replica) {
+        if (fold.Ly % BY == 0 && ny % fold.Ly == 0) { ord.yrep = ny / fold.Ly; ord.yper = fold.Ly / BY; }
+        if (fold.kphase == 0 && fold.Lz % BZ == 0 && nk % fold.Lz == 0 && (long long)nyb * (nk / fold.Lz) <= 65535) {
+            ord.zrep = nk / fold.Lz; ord.zper = fold.Lz / BZ;
+        }
+    }
+    dim3 grid((nx + 127) / 128, nyb * ord.zrep, ord.zper);
+    kern<<<grid, NT, smem, st>>>(t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, ord, out);
+    return 1;
+}
+
 // brick shapes (BY, BZ, threads); WN_BRICK=<index> overrides the default for tuning runs
 struct Shape { int by, bz, nt; };
 const Shape kShapes[] = { {16, 8, 256}, {16, 16, 256}, {8, 8, 256}, {8, 16, 256}, {8, 4, 256}, {16, 4, 256},
@@ -604,8 +803,24 @@ int brick_pass(WnTileView t, const WnTabs &tabs, const float *hy, const float *h
 {
     int pick = forced_shape();
     BrickPlan plan{false, 0, 0};
-    // the float4 kernel needs 16-byte aligned rows of the output and of the period block
+    // the float4 kernels need 16-byte aligned rows of the output and of the period block
     const bool can4 = (nx % 4 == 0) && (!fold.P || fold.Lx % 4 == 0);
+    // one or two bands left after folding: the z-streaming kernel (WN_COL4=0 disables it for A/B runs)
+    const char *col4_env = getenv("WN_COL4");
+    const bool col4_on = !col4_env || atoi(col4_env) != 0;
+    if (pick < 0 && can4 && col4_on && b.nbands >= 1 && b.nbands <= 2 && (ny + 7) / 8 <= 65535 && (nk + 31) / 32 <= 65535) {
+        plan = plan_bricks(hy, ny, hz, nk, b, 8, 32, 128, true);
+        if (plan.ok && plan.smem <= 56 * 1024) {
+            // ring of 8 period-block planes per thread (32 KB) while four CTAs still fit an SM, else 4 planes
+            int ring = plan.smem <= 24 * 1024 ? 8 : 4;
+            if (const char *e = getenv("WN_RING")) ring = atoi(e) == 4 ? 4 : 8;
+            if (b.nbands == 1)
+                return ring == 8 ? launch_col4<1, 8>(t, tabs, nx, ny, nk, out, plan, fold, st)
+                                 : launch_col4<1, 4>(t, tabs, nx, ny, nk, out, plan, fold, st);
+            return ring == 8 ? launch_col4<2, 8>(t, tabs, nx, ny, nk, out, plan, fold, st)
+                             : launch_col4<2, 4>(t, tabs, nx, ny, nk, out, plan, fold, st);
+        }
+    }
     if (pick >= kFirstShape4 && !can4) pick = -1;
     if (pick >= 0) {                                           // forced shape (tuning): only where it fits
         plan = plan_bricks(hy, ny, hz, nk, b, kShapes[pick].by, kShapes[pick].bz, pick >= kFirstShape4 ? 128 : 32,
@@ -717,7 +932,8 @@ WnTabs plan_tabs(const WnFastPlan *plan, const unsigned char *rows, int nb, int 
     tb.x = plan->tab; tb.y = tb.x + (size_t)plan->tab_bands * plan->sx; tb.z = tb.y + (size_t)plan->tab_bands * plan->sy;
     tb.sx = plan->sx; tb.sy = plan->sy; tb.sz = plan->sz;
     tb.kz0 = kz0; tb.nb = nb;
-    for (int i = 0; i < WN_MAX_BANDS; ++i) tb.row[i] = i < nb ? rows[i] : 0;
+    tb.rowbits = 0;
+    for (int i = 0; i < nb; ++i) tb.rowbits |= (unsigned long long)(rows[i] & 15) << (4 * i);
     return tb;
 }
 
@@ -749,7 +965,7 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
     }
     if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
     const long long total = (long long)nx * ny * nz;
-    long long budget = 1LL << 24;                              // samples in the period block: 64 MiB, L2 resident
+    long long budget = 1LL << 27;                              // samples in the period block: 512 MiB of scratch at most
     if (const char *e = getenv("WN_FOLD_BUDGET")) budget = atoll(e);
     struct Cand { int band; int px, py, pz; long long vol; };
     std::vector<Cand> cand;
