@@ -28,6 +28,21 @@ def test_slab_ranges_cover_and_balance():
         sh.slab_range(10, 3, 3)
 
 
+def test_cyclic_indices_partition_the_axis():
+    sh = wnpkg.load_sub("sharding")
+    for total, world, chunk in ((1024, 8, 32), (1024, 2, 32), (1000, 3, 32), (70, 4, 8), (5, 8, 32), (0, 2, 32), (64, 1, 32)):
+        parts = [sh.cyclic_slab_indices(total, r, world, chunk) for r in range(world)]
+        allidx = np.sort(np.concatenate(parts))
+        assert np.array_equal(allidx, np.arange(total))
+        for part in parts:
+            assert np.all(np.diff(part) > 0)
+    # 1024 slices on 8 ranks: rank 3 owns chunks 3, 11, 19, 27
+    got = sh.cyclic_slab_indices(1024, 3, 8)
+    assert len(got) == 128 and got[0] == 96 and got[32] == 96 + 256 and got[-1] == 96 + 768 + 31
+    with pytest.raises(ValueError):
+        sh.cyclic_slab_indices(10, 2, 2)
+
+
 def test_config3_parameters():
     sh = wnpkg.load_sub("sharding")
     ax = sh.lattice_axes_config3(1024)
@@ -58,11 +73,15 @@ def _worker(rank, world, port, tmpdir):
         local = full[b:e].clone()
         # (3) gather for file output
         got = sh.gather_slabs(local, nz, nx * ny, rank, world, 0)
+        # (4) the same with block-cyclic shards (chunks of 2 slices dealt round-robin)
+        idx = torch.from_numpy(sh.cyclic_slab_indices(nz, rank, world, chunk=2))
+        got_c = sh.gather_cyclic(full[idx].clone(), nz, nx * ny, rank, world, 0, chunk=2)
         if rank == 0:
             assert torch.equal(got.reshape(nz, ny, nx), full)
+            assert torch.equal(got_c.reshape(nz, ny, nx), full)
             open(os.path.join(tmpdir, "ok"), "w").write("1")
         else:
-            assert got is None
+            assert got is None and got_c is None
     finally:
         dist.destroy_process_group()
 

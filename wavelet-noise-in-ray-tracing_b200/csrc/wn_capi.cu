@@ -754,7 +754,10 @@ extern "C" int wn_multiband3d_lattice(const wn_tile *t, const float *xs, int nx,
     }
     WnFastPlan plan;
     int np = wn_mb3d_fast_prepare(tv, L, xs, ys, zs, b, &plan, c->stream);
-    if (np < 0) return wn_fail(WN_ECUDA, "fast lattice prepare failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (np < 0) {
+        wn_mb3d_fast_finish(&plan, c->stream);
+        return wn_fail(WN_ECUDA, "fast lattice prepare failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     c->launches += (uint64_t)np;
     if (space == WN_DEVICE)
         r = run_device(c, [&](cudaStream_t st) { return wn_mb3d_fast_run(tv, L, ys, zs, b, nullptr, &plan, 0, nz, out, st); });

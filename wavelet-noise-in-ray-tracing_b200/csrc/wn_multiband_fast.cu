@@ -697,31 +697,84 @@ k_mb3d_gather(WnTileView t, WnTabs tabs, int nx, int ny, int nk, float *__restri
     out[(size_t)i + (size_t)nx * ((size_t)j + (size_t)ny * k)] = acc;
 }
 
-// host-side plan: first tap cells with exactly the device formula (this TU's host code is built with
-// -ffp-contract=off), monotonicity of y/z and the largest Ey*Ez any brick needs.
-inline int first_cell(float coord, float scale) { return (int)std::ceil(coord * scale - 0.5f) - 1; }
+// ---- host-side tables of one call ------------------------------------------------------------------------------
+// Entry of every coordinate of every band, computed once per top-level call with exactly the device formula (this
+// TU's host code is built with -ffp-contract=off): the weights (compared bitwise by the period detection), the first
+// tap cell reduced mod n, and the unwrapped first tap cell (brick footprints).  Period blocks are prefixes of the
+// axes, so every nesting level reads the same tables.
+struct HostEntry {
+    float w0, w1, w2;
+    int cell;
+    bool operator==(const HostEntry &o) const
+    {
+        return std::memcmp(&w0, &o.w0, 3 * sizeof(float)) == 0 && cell == o.cell;
+    }
+};
 
+struct HostAxes {
+    int nb = 0, nx = 0, ny = 0, nz = 0;
+    std::vector<HostEntry> e;       // [band][x | y | z]
+    std::vector<int> first;         // unwrapped first tap cell, same layout
+    size_t per_band() const { return (size_t)nx + ny + nz; }
+    const HostEntry *ex(int row) const { return e.data() + row * per_band(); }
+    const HostEntry *ey(int row) const { return ex(row) + nx; }
+    const HostEntry *ez(int row) const { return ey(row) + ny; }
+    const int *fy(int row) const { return first.data() + row * per_band() + nx; }
+    const int *fz(int row) const { return fy(row) + ny; }
+};
+
+inline void host_entry(float coord, float scale, int n, HostEntry &e, int &first)   // mirrors axis_entry()
+{
+    const float a = coord * scale - 0.5f;
+    const int mid = (int)std::ceil(a);
+    const float tt = (float)mid - a;
+    e.w0 = tt * tt * 0.5f;
+    const float s1 = 1.0f - tt;
+    e.w2 = s1 * s1 * 0.5f;
+    e.w1 = 1.0f - e.w0 - e.w2;
+    first = mid - 1;
+    const int m = first % n;
+    e.cell = m < 0 ? m + n : m;
+}
+
+HostAxes *make_host_axes(const float *xs, int nx, const float *ys, int ny, const float *zs, int nz, const WnBands &b, int n)
+{
+    HostAxes *h = new HostAxes;
+    h->nb = b.nbands; h->nx = nx; h->ny = ny; h->nz = nz;
+    h->e.resize(h->per_band() * b.nbands);
+    h->first.resize(h->per_band() * b.nbands);
+    for (int band = 0; band < b.nbands; ++band) {
+        HostEntry *e = h->e.data() + band * h->per_band();
+        int *f = h->first.data() + band * h->per_band();
+        const float s = b.scale[band];
+        for (int i = 0; i < nx; ++i) host_entry(xs[i], s, n, e[i], f[i]);
+        for (int i = 0; i < ny; ++i) host_entry(ys[i], s, n, e[nx + i], f[nx + i]);
+        for (int i = 0; i < nz; ++i) host_entry(zs[i], s, n, e[nx + ny + i], f[nx + ny + i]);
+    }
+    return h;
+}
+
+// brick plan of a lattice window (y in [0, ny), z in [k0, k0 + nk)) for the bands with table rows rows[0..nb):
+// monotonicity of the y/z tap cells and the largest Ey*Ez any brick needs
 struct BrickPlan { bool ok; size_t smem; int max_rows; };
 
-BrickPlan plan_bricks(const float *ys, int ny, const float *zs, int nk, const WnBands &b, int BY, int BZ, int BX = 32,
-                      bool all_bands_resident = false)
+BrickPlan plan_bricks(const HostAxes &h, const unsigned char *rows, int nb, int ny, int k0, int nk, int BY, int BZ,
+                      int BX = 32, bool all_bands_resident = false)
 {
     BrickPlan p{true, 0, 0};
-    std::vector<int> my(ny), mz(nk);
-    for (int band = 0; band < b.nbands; ++band) {
-        for (int j = 0; j < ny; ++j) my[j] = first_cell(ys[j], b.scale[band]);
-        for (int k = 0; k < nk; ++k) mz[k] = first_cell(zs[k], b.scale[band]);
+    for (int band = 0; band < nb; ++band) {
+        const int *my = h.fy(rows[band]), *mz = h.fz(rows[band]) + k0;
         for (int j = 1; j < ny; ++j) if (my[j] < my[j - 1]) { p.ok = false; return p; }
         for (int k = 1; k < nk; ++k) if (mz[k] < mz[k - 1]) { p.ok = false; return p; }
         long long ey = 0, ez = 0;
         for (int j0 = 0; j0 < ny; j0 += BY) ey = std::max<long long>(ey, (long long)my[std::min(j0 + BY, ny) - 1] - my[j0] + 3);
-        for (int k0 = 0; k0 < nk; k0 += BZ) ez = std::max<long long>(ez, (long long)mz[std::min(k0 + BZ, nk) - 1] - mz[k0] + 3);
+        for (int kb = 0; kb < nk; kb += BZ) ez = std::max<long long>(ez, (long long)mz[std::min(kb + BZ, nk) - 1] - mz[kb] + 3);
         if (ey * ez * BX > 1500 * 32) { p.ok = false; return p; }       // U must stay below ~192 KB
         const int rows_b = (int)((ey * ez + 3) & ~3LL);
         p.max_rows = all_bands_resident ? p.max_rows + rows_b : std::max(p.max_rows, rows_b);
     }
     if ((long long)p.max_rows * BX > 1500 * 32) { p.ok = false; return p; }
-    p.smem = (size_t)p.max_rows * (BX * sizeof(float) + sizeof(int)) + (size_t)b.nbands * (BX + BY + BZ) * sizeof(float4);
+    p.smem = (size_t)p.max_rows * (BX * sizeof(float) + sizeof(int)) + (size_t)nb * (BX + BY + BZ) * sizeof(float4);
     return p;
 }
 
@@ -796,9 +849,10 @@ int forced_shape()
     return -1;
 }
 
-// One brick-kernel pass over a lattice window (host copies hy/hz of the window's y/z axes for planning).
+// One brick-kernel pass over the lattice window y in [0, ny), z in [k0, k0 + nk) (h: the call's host tables, rows: the
+// table rows of the bands in b).
 // Returns kernels launched, or -1 when the lattice does not qualify (unsorted y/z, footprint too large, ...).
-int brick_pass(WnTileView t, const WnTabs &tabs, const float *hy, const float *hz,
+int brick_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsigned char *rows, int k0,
                int nx, int ny, int nk, const WnBands &b, WnFold fold, float *out, cudaStream_t st)
 {
     int pick = forced_shape();
@@ -809,7 +863,7 @@ int brick_pass(WnTileView t, const WnTabs &tabs, const float *hy, const float *h
     const char *col4_env = getenv("WN_COL4");
     const bool col4_on = !col4_env || atoi(col4_env) != 0;
     if (pick < 0 && can4 && col4_on && b.nbands >= 1 && b.nbands <= 2 && (ny + 7) / 8 <= 65535 && (nk + 31) / 32 <= 65535) {
-        plan = plan_bricks(hy, ny, hz, nk, b, 8, 32, 128, true);
+        plan = plan_bricks(h, rows, b.nbands, ny, k0, nk, 8, 32, 128, true);
         if (plan.ok && plan.smem <= 56 * 1024) {
             // ring of 8 period-block planes per thread (32 KB) while four CTAs still fit an SM, else 4 planes
             int ring = plan.smem <= 24 * 1024 ? 8 : 4;
@@ -823,22 +877,22 @@ int brick_pass(WnTileView t, const WnTabs &tabs, const float *hy, const float *h
     }
     if (pick >= kFirstShape4 && !can4) pick = -1;
     if (pick >= 0) {                                           // forced shape (tuning): only where it fits
-        plan = plan_bricks(hy, ny, hz, nk, b, kShapes[pick].by, kShapes[pick].bz, pick >= kFirstShape4 ? 128 : 32,
+        plan = plan_bricks(h, rows, b.nbands, ny, k0, nk, kShapes[pick].by, kShapes[pick].bz, pick >= kFirstShape4 ? 128 : 32,
                            pick >= kFirstShape4);
         if (!plan.ok || plan.smem > 100 * 1024) pick = -1;
     }
     if (pick < 0) {
         if (can4) {
             pick = kFirstShape4;                               // 128 x 8 x 8 samples, small footprints only
-            plan = plan_bricks(hy, ny, hz, nk, b, kShapes[pick].by, kShapes[pick].bz, 128, true);
+            plan = plan_bricks(h, rows, b.nbands, ny, k0, nk, kShapes[pick].by, kShapes[pick].bz, 128, true);
         }
         if (!plan.ok || plan.smem > 72 * 1024) {
             pick = 0;                                          // 32 x 16 x 8 samples
-            plan = plan_bricks(hy, ny, hz, nk, b, kShapes[0].by, kShapes[0].bz);
+            plan = plan_bricks(h, rows, b.nbands, ny, k0, nk, kShapes[0].by, kShapes[0].bz);
         }
         if (!plan.ok || plan.smem > 56 * 1024) {               // big footprints: halve the brick in z
             pick = kDefaultShape;
-            plan = plan_bricks(hy, ny, hz, nk, b, kShapes[pick].by, kShapes[pick].bz);
+            plan = plan_bricks(h, rows, b.nbands, ny, k0, nk, kShapes[pick].by, kShapes[pick].bz);
         }
     }
     const int BY = kShapes[pick].by, BZ = kShapes[pick].bz;
@@ -866,36 +920,10 @@ int brick_pass(WnTileView t, const WnTabs &tabs, const float *hy, const float *h
 // with period P along the axis.  Such bands are evaluated once on their common period block (Lx x Ly x Lz samples,
 // by the same brick kernel) and added by index mod period in the main kernel's epilogue.  Detection is exact
 // (bitwise on the table entries the device will compute), so arbitrary coordinates simply do not fold.
-struct HostEntry {
-    float w0, w1, w2;
-    int cell;
-    bool operator==(const HostEntry &o) const
-    {
-        return std::memcmp(&w0, &o.w0, 3 * sizeof(float)) == 0 && cell == o.cell;
-    }
-};
-
-inline HostEntry host_entry(float coord, float scale, int n)          // mirrors axis_entry(), cell reduced mod n
-{
-    const float a = coord * scale - 0.5f;
-    const int mid = (int)std::ceil(a);
-    const float tt = (float)mid - a;
-    HostEntry e;
-    e.w0 = tt * tt * 0.5f;
-    const float s1 = 1.0f - tt;
-    e.w2 = s1 * s1 * 0.5f;
-    e.w1 = 1.0f - e.w0 - e.w2;
-    int m = (mid - 1) % n;
-    e.cell = m < 0 ? m + n : m;
-    return e;
-}
-
 // smallest P <= len/2 with entry[i+P] == entry[i] for all i; len when the axis is not periodic
-int axis_period(const float *xs, int len, float scale, int n)
+int axis_period(const HostEntry *e, int len)
 {
     if (len < 4) return len;
-    std::vector<HostEntry> e(len);
-    for (int i = 0; i < len; ++i) e[i] = host_entry(xs[i], scale, n);
     for (int P = 1; P <= len / 2; ++P) {
         if (!(e[P] == e[0])) continue;
         bool ok = true;
@@ -952,18 +980,21 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
     if (depth == 0) {
         plan->tab = nullptr;
         plan->owns_tab = 0;
+        plan->host_axes = nullptr;
         plan->tab_bands = b.nbands; plan->sx = nx; plan->sy = ny; plan->sz = nz;
         for (int i = 0; i < WN_MAX_BANDS; ++i) plan->direct_rows[i] = (unsigned char)i;
+        plan->owns_tab = 1;
+        plan->host_axes = make_host_axes(h_xs, std::max(nx, 0), h_ys, std::max(ny, 0), h_zs, std::max(nz, 0), b, t.n);
         if (nx <= 0 || ny <= 0 || nz <= 0 || b.nbands <= 0) return 0;
         const size_t per_band = (size_t)nx + ny + nz;
         if (cudaMallocAsync(&plan->tab, per_band * b.nbands * sizeof(float4), st) != cudaSuccess) return -1;
-        plan->owns_tab = 1;
         float4 *tx = plan->tab, *ty = tx + (size_t)b.nbands * nx, *tz = ty + (size_t)b.nbands * ny;
         const int total_e = (int)(per_band * b.nbands);
         k_axis_tables<<<std::min((total_e + 255) / 256, 1184), 256, 0, st>>>(c, b, 0, nz, tx, ty, tz);
         launched = 1;
     }
     if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
+    const HostAxes &hax = *static_cast<const HostAxes *>(plan->host_axes);
     const long long total = (long long)nx * ny * nz;
     long long budget = 1LL << 27;                              // samples in the period block: 512 MiB of scratch at most
     if (const char *e = getenv("WN_FOLD_BUDGET")) budget = atoll(e);
@@ -984,17 +1015,21 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
     }
     if (budget > 0)
         for (int i = 0; i < b.nbands; ++i) {
-            Cand cd{i, axis_period(h_xs, nx, b.scale[i], t.n), axis_period(h_ys, ny, b.scale[i], t.n),
-                    axis_period(h_zs, nz, b.scale[i], t.n), 0};
+            const int row = plan->direct_rows[i];
+            Cand cd{i, axis_period(hax.ex(row), nx), axis_period(hax.ey(row), ny), axis_period(hax.ez(row), nz), 0};
             cd.vol = (long long)cd.px * cd.py * cd.pz;
             if (cd.vol * 4 <= total) cand.push_back(cd);
         }
     std::sort(cand.begin(), cand.end(), [](const Cand &a, const Cand &b2) { return a.vol < b2.vol; });
-    // grow the folded set in order of period volume; keep the prefix with the lowest estimated cost
-    //   cost = sum_direct c_b * total + sum_folded c_b * block + 0.3 * total (the add) 
+    // grow the folded set in order of period volume; keep the prefix with the lowest estimated cost.  Period blocks
+    // nest (the block is evaluated by this same function), so band i of the prefix is charged on the block it
+    // enlarges the fold to, plus the add of the previous level:
+    //   cost = (sum_direct c_b + 0.3) * total + sum_{i folded} ((c_i + 0.3) * block_i + level)
+    // in units of one band-sample (~1 ps of GPU time); level = the latency of one more small dependent launch (~8 us).
+    const double level_overhead = 8e6;
     double direct_sum = 0.0;
     for (int i = 0; i < b.nbands; ++i) direct_sum += cost[i];
-    double best = direct_sum * (double)total, folded_sum = 0.0;
+    double best = direct_sum * (double)total, nested_sum = 0.0;
     long long Lx = 1, Ly = 1, Lz = 1, bLx = 1, bLy = 1, bLz = 1;
     bool folded[WN_MAX_BANDS] = { false }, trial[WN_MAX_BANDS] = { false };
     int nfold = 0, ntrial = 0;
@@ -1005,9 +1040,9 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
         Lx = lx; Ly = ly; Lz = lz;
         trial[cd.band] = true;
         ++ntrial;
-        folded_sum += cost[cd.band];
+        nested_sum += (cost[cd.band] + 0.3) * (double)(Lx * Ly * Lz) + level_overhead;
         direct_sum -= cost[cd.band];
-        const double est = direct_sum * (double)total + folded_sum * (double)(Lx * Ly * Lz) + 0.3 * (double)total;
+        const double est = (direct_sum + 0.3) * (double)total + nested_sum;
         if (est < best) {
             best = est;
             for (int i = 0; i < b.nbands; ++i) folded[i] = trial[i];
@@ -1054,7 +1089,9 @@ void wn_mb3d_fast_finish(WnFastPlan *plan, cudaStream_t st)
     if (plan->P) cudaFreeAsync(plan->P, st);
     plan->P = nullptr;
     if (plan->owns_tab && plan->tab) cudaFreeAsync(plan->tab, st);
+    if (plan->owns_tab) delete static_cast<HostAxes *>(plan->host_axes);
     plan->tab = nullptr;
+    plan->host_axes = nullptr;
     plan->owns_tab = 0;
 }
 
@@ -1064,10 +1101,11 @@ int wn_mb3d_fast_run(WnTileView t, WnLattice c, const float *h_ys, const float *
 {
     if (nk <= 0 || c.nx <= 0 || c.ny <= 0) return 0;
     const int nx = c.nx, ny = c.ny;
-    const float *hz = h_zs + k0;
+    (void)h_ys; (void)h_zs;
+    const HostAxes &hax = *static_cast<const HostAxes *>(plan->host_axes);
     const WnFold fold = make_fold(plan->P, plan->Lx, plan->Ly, plan->Lz, plan->P ? k0 % plan->Lz : 0);
     const WnTabs tabs = plan_tabs(plan, plan->direct_rows, plan->direct.nbands, k0);
-    const int r = brick_pass(t, tabs, h_ys, hz, nx, ny, nk, plan->direct, fold, out, st);
+    const int r = brick_pass(t, tabs, hax, plan->direct_rows, k0, nx, ny, nk, plan->direct, fold, out, st);
     if (r >= 0) return r;
 
     // ---- generic path (unsorted y/z axes or huge steps): every band by direct gathers, no folding

@@ -1,7 +1,8 @@
 """Multi-GPU plumbing: one process per GPU, samples sharded with no data-path exchange.
 
 The path shards naturally: every sample reads only the replicated, read-only tile,
-so a volume is cut into contiguous z-slabs and an image into contiguous row-bands; the only collectives are
+so a volume is cut into z-slabs (contiguous, or block-cyclic chunks -- see cyclic_slab_indices) and an image into
+contiguous row-bands; the only collectives are
   (1) one broadcast of the finished tile from rank 0 (8 MiB at n=128) -- NCCL over NVLink on GPUs, and
   (2) an optional gather of the output shards to rank 0 when a file has to be written.
 `torch.distributed` is plumbing only; with backend "gloo" the same code runs on CPU buffers, which is how
@@ -21,6 +22,26 @@ def slab_range(total, rank, world):
 
 def all_slabs(total, world):
     return [slab_range(total, r, world) for r in range(world)]
+
+
+CYCLIC_CHUNK = 32       # z slices per chunk = the z extent of one CTA brick of the fast lattice kernel
+
+
+def cyclic_slab_indices(total, rank, world, chunk=CYCLIC_CHUNK):
+    """Block-cyclic sharding of an axis: chunks of `chunk` consecutive units are dealt round-robin, rank r owns chunks
+    r, r+world, r+2*world, ...  Returns the owned indices (int64, ascending).
+
+    Why not contiguous slabs: the fast lattice kernel evaluates a band whose samples repeat with the tile period only
+    once per period (periodic folding).  A contiguous slab of 1024/8 slices is shorter than the
+    z periods of the low bands, so that saving would be lost as the rank count grows; a block-cyclic slab keeps slices
+    that are congruent modulo those periods on the same rank, so every rank folds the same bands as the single-GPU run
+    and its work stays 1/world of it.  Each sample still depends on the replicated tile only: no exchange."""
+    if world <= 0 or not (0 <= rank < world) or chunk <= 0:
+        raise ValueError(f"bad rank/world/chunk {rank}/{world}/{chunk}")
+    total = int(total)
+    nchunks = (total + chunk - 1) // chunk
+    parts = [np.arange(c * chunk, min((c + 1) * chunk, total), dtype=np.int64) for c in range(rank, nchunks, world)]
+    return np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
 
 
 def dist_info():
@@ -85,6 +106,31 @@ def gather_slabs(local, total, axis_len_other, rank=None, world=None, dst=0):
     if rank != dst:
         return None
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)])
+
+
+def gather_cyclic(local, total, axis_len_other, rank=None, world=None, dst=0, chunk=CYCLIC_CHUNK):
+    """gather_slabs for block-cyclic shards: rank r holds the slices cyclic_slab_indices(total, r, world, chunk) in
+    ascending order; dst gets them back in axis order."""
+    import torch
+    import torch.distributed as dist
+    if rank is None:
+        rank, world, _ = dist_info()
+    idx = [cyclic_slab_indices(total, r, world, chunk) for r in range(world)]
+    pad = max(len(i) for i in idx) * axis_len_other
+    send = torch.zeros(pad, dtype=local.dtype, device=local.device)
+    send[: local.numel()] = local.reshape(-1)
+    if dist.get_backend() == "nccl":
+        bufs = [torch.empty(pad, dtype=local.dtype, device=local.device) for _ in range(world)]
+        dist.all_gather(bufs, send)
+    else:
+        bufs = [torch.empty(pad, dtype=local.dtype, device=local.device) for _ in range(world)] if rank == dst else None
+        dist.gather(send, bufs, dst=dst)
+    if rank != dst:
+        return None
+    full = torch.empty((total, axis_len_other), dtype=local.dtype, device=local.device)
+    for i, b in zip(idx, bufs):
+        full[torch.from_numpy(i).to(local.device)] = b[: len(i) * axis_len_other].reshape(len(i), axis_len_other)
+    return full.reshape(-1)
 
 
 def lattice_axes_config3(size=1024, base_range=4.0):
