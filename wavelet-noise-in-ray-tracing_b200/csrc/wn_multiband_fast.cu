@@ -47,9 +47,20 @@ struct WnTabs {
     int kz0;                    // first z entry of this launch
     int nb;                     // bands of this launch
     unsigned long long rowbits;  // table row of band b in bits [4b, 4b+4): no indexed kernel parameter, no local copy
+    int wait_first;             // first kernel after k_axis_tables: must wait for its predecessor before reading the tables
 };
 static_assert(WN_MAX_BANDS <= 16, "rows are packed four bits each");
 __host__ __device__ __forceinline__ int tabs_row(const WnTabs &t, int b) { return (int)((t.rowbits >> (4 * b)) & 15ull); }
+
+// Programmatic dependent launch.  The kernels of a call are a chain of dependent launches, several of them tiny
+// (period blocks of a few CTAs), and back-to-back calls continue the chain.  Each launch carries the programmatic
+// stream serialisation attribute, so its CTAs may start while the previous kernel drains and run the part that does
+// not depend on it (tables from two kernels back, footprints, the X pass from the constant tile) up to
+// chain_wait(), which returns once the previous kernel has completed and its writes are visible.  Every kernel
+// releases its dependents only AFTER its own wait, so "my predecessor's predecessor is complete" holds at every
+// start, and no kernel writes global memory before its wait (stream-ordered scratch may be reused across calls).
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void chain_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 inline WnFold make_fold(const float *P, int Lx, int Ly, int Lz, int kphase)
 {
@@ -83,6 +94,8 @@ __device__ __forceinline__ float4 axis_entry(float q, float wscale)
 __global__ void k_axis_tables(WnLattice c, WnBands b, int k0, int nk, float4 *__restrict__ tx, float4 *__restrict__ ty,
                               float4 *__restrict__ tz)
 {
+    chain_wait();
+    chain_release();
     const int per_band = c.nx + c.ny + nk;
     const int total = per_band * b.nbands;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -119,6 +132,7 @@ k_mb3d_brick(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, in
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = blockIdx.x * 32, j0 = blockIdx.y * BY, k0 = blockIdx.z * BZ;
     const int pitch = n + WN_TILE_PAD;
+    if (tabs.wait_first) { chain_wait(); chain_release(); }
 
     // ---- phase 0: every table entry of every band in one round of independent loads (64 threads per band)
     {
@@ -220,6 +234,7 @@ k_mb3d_brick(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, in
         if (b + 1 < nbands) __syncthreads();
     }
 
+    if (!tabs.wait_first) { chain_wait(); chain_release(); }   // the period block is the previous kernel's output
     const int i = i0 + lane;
     if (i < nx) {
         const size_t plane = (size_t)nx * ny;
@@ -426,6 +441,7 @@ k_mb3d_brick4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, i
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY, k0 = blockIdx.z * BZ;
+    if (tabs.wait_first) { chain_wait(); chain_release(); }
 
     q4_load_tables<BY, BZ, NT>(s_tab, tabs, i0, j0, k0, nx, ny, nk);
     __shared__ Q4Foot ft;
@@ -477,6 +493,7 @@ k_mb3d_brick4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, i
     }
 
     // ---- epilogue (host guarantees nx % 4 == 0 and, when folding, Lx % 4 == 0): float4 loads and stores
+    if (!tabs.wait_first) { chain_wait(); chain_release(); }   // the period block is the previous kernel's output
     const int i = i0 + 4 * lane;
     if (i < nx) {
         const size_t plane = (size_t)nx * ny;
@@ -547,6 +564,8 @@ k_mb3d_col4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int
     float4 *s_tab = smem4 + max_rows * 32;
     int *s_rowoff = reinterpret_cast<int *>(s_tab + NB * PER_BAND);
 
+    chain_wait();                                              // the ring prefetch below reads the previous kernel's output
+    chain_release();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int yb, zb;
     {
@@ -662,6 +681,8 @@ __global__ void k_pad_tile(const float *__restrict__ N, float *__restrict__ P, i
 __global__ void __launch_bounds__(256)
 k_mb3d_gather(WnTileView t, WnTabs tabs, int nx, int ny, int nk, float *__restrict__ out)
 {
+    chain_wait();
+    chain_release();
     const int nbands = tabs.nb;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y, k = blockIdx.z;
@@ -713,6 +734,7 @@ struct HostEntry {
 
 struct HostAxes {
     int nb = 0, nx = 0, ny = 0, nz = 0;
+    mutable int runs = 0;           // lattice kernels launched so far in this call (the first one follows k_axis_tables)
     std::vector<HostEntry> e;       // [band][x | y | z]
     std::vector<int> first;         // unwrapped first tap cell, same layout
     size_t per_band() const { return (size_t)nx + ny + nz; }
@@ -778,6 +800,21 @@ BrickPlan plan_bricks(const HostAxes &h, const unsigned char *rows, int nb, int 
     return p;
 }
 
+// launch with the programmatic stream serialisation attribute (WN_PDL=0: plain stream order, for A/B runs)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    static const bool pdl = [] { const char *e = getenv("WN_PDL"); return !e || atoi(e) != 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int BY, int BZ, int NT>
 int launch_brick(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
                  float *out, const BrickPlan &plan, WnFold fold, cudaStream_t st)
@@ -787,7 +824,7 @@ int launch_brick(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     dim3 grid((nx + 31) / 32, (ny + BY - 1) / BY, (nk + BZ - 1) / BZ);
-    kern<<<grid, NT, smem, st>>>(t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, out);
+    launch_chained(kern, grid, dim3(NT), smem, st, t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, out);
     return 1;
 }
 
@@ -800,7 +837,7 @@ int launch_brick4(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     dim3 grid((nx + 127) / 128, (ny + BY - 1) / BY, (nk + BZ - 1) / BZ);
-    kern<<<grid, NT, smem, st>>>(t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, out);
+    launch_chained(kern, grid, dim3(NT), smem, st, t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, out);
     return 1;
 }
 
@@ -826,7 +863,7 @@ int launch_col4(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
         }
     }
     dim3 grid((nx + 127) / 128, nyb * ord.zrep, ord.zper);
-    kern<<<grid, NT, smem, st>>>(t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, ord, out);
+    launch_chained(kern, grid, dim3(NT), smem, st, t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, ord, out);
     return 1;
 }
 
@@ -960,6 +997,7 @@ WnTabs plan_tabs(const WnFastPlan *plan, const unsigned char *rows, int nb, int 
     tb.x = plan->tab; tb.y = tb.x + (size_t)plan->tab_bands * plan->sx; tb.z = tb.y + (size_t)plan->tab_bands * plan->sy;
     tb.sx = plan->sx; tb.sy = plan->sy; tb.sz = plan->sz;
     tb.kz0 = kz0; tb.nb = nb;
+    tb.wait_first = 1;
     tb.rowbits = 0;
     for (int i = 0; i < nb; ++i) tb.rowbits |= (unsigned long long)(rows[i] & 15) << (4 * i);
     return tb;
@@ -990,7 +1028,7 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
         if (cudaMallocAsync(&plan->tab, per_band * b.nbands * sizeof(float4), st) != cudaSuccess) return -1;
         float4 *tx = plan->tab, *ty = tx + (size_t)b.nbands * nx, *tz = ty + (size_t)b.nbands * ny;
         const int total_e = (int)(per_band * b.nbands);
-        k_axis_tables<<<std::min((total_e + 255) / 256, 1184), 256, 0, st>>>(c, b, 0, nz, tx, ty, tz);
+        launch_chained(k_axis_tables, dim3(std::min((total_e + 255) / 256, 1184)), dim3(256), 0, st, c, b, 0, nz, tx, ty, tz);
         launched = 1;
     }
     if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
@@ -1104,7 +1142,8 @@ int wn_mb3d_fast_run(WnTileView t, WnLattice c, const float *h_ys, const float *
     (void)h_ys; (void)h_zs;
     const HostAxes &hax = *static_cast<const HostAxes *>(plan->host_axes);
     const WnFold fold = make_fold(plan->P, plan->Lx, plan->Ly, plan->Lz, plan->P ? k0 % plan->Lz : 0);
-    const WnTabs tabs = plan_tabs(plan, plan->direct_rows, plan->direct.nbands, k0);
+    WnTabs tabs = plan_tabs(plan, plan->direct_rows, plan->direct.nbands, k0);
+    tabs.wait_first = hax.runs++ == 0;
     const int r = brick_pass(t, tabs, hax, plan->direct_rows, k0, nx, ny, nk, plan->direct, fold, out, st);
     if (r >= 0) return r;
 
@@ -1114,6 +1153,6 @@ int wn_mb3d_fast_run(WnTileView t, WnLattice c, const float *h_ys, const float *
     for (int i = 0; i < WN_MAX_BANDS; ++i) ident[i] = (unsigned char)i;
     const WnTabs all = plan_tabs(plan, all_rows ? all_rows : ident, all_bands.nbands, k0);
     dim3 grid((nx + 255) / 256, ny, nk);
-    k_mb3d_gather<<<grid, 256, 0, st>>>(t, all, nx, ny, nk, out);
+    launch_chained(k_mb3d_gather, grid, dim3(256), 0, st, t, all, nx, ny, nk, out);
     return 1;
 }
