@@ -17,14 +17,15 @@ sh = importlib.import_module("wavelet-noise-in-ray-tracing_b200.sharding")
 nz = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 KNOBS = ("WN_COL4", "WN_FOLD_BUDGET", "WN_REPLICA_ORDER", "WN_BRICK", "WN_RING")
 VARIANTS = [
-    ("brick4, 64 MiB block", {"WN_COL4": "0", "WN_FOLD_BUDGET": str(1 << 24)}),
-    ("col4,   64 MiB block", {"WN_COL4": "1", "WN_FOLD_BUDGET": str(1 << 24)}),
-    ("brick4, 512 MiB block", {"WN_COL4": "0", "WN_FOLD_BUDGET": str(1 << 27)}),
-    ("col4,   512 MiB block (default)", {"WN_COL4": "1", "WN_FOLD_BUDGET": str(1 << 27)}),
-    ("col4,   512 MiB block, ring 4", {"WN_COL4": "1", "WN_FOLD_BUDGET": str(1 << 27), "WN_RING": "4"}),
-    ("col4,   512 MiB block, ring 8", {"WN_COL4": "1", "WN_FOLD_BUDGET": str(1 << 27), "WN_RING": "8"}),
-    ("col4,   512 MiB block, replica order", {"WN_COL4": "1", "WN_FOLD_BUDGET": str(1 << 27), "WN_REPLICA_ORDER": "1"}),
-    ("no folding, col4 off", {"WN_COL4": "0", "WN_FOLD_BUDGET": "0"}),
+    ("default (col4, 512 MiB block, ring 8)", {}),
+    ("ring 4", {"WN_RING": "4"}),
+    ("register look-ahead 2", {"WN_RING": "-2"}),
+    ("register look-ahead 4", {"WN_RING": "-4"}),
+    ("plain block order", {"WN_REPLICA_ORDER": "0"}),
+    ("64 MiB block", {"WN_FOLD_BUDGET": str(1 << 24)}),
+    ("brick4 main kernel", {"WN_COL4": "0"}),
+    ("brick4, 64 MiB block (round-1 midpoint)", {"WN_COL4": "0", "WN_FOLD_BUDGET": str(1 << 24)}),
+    ("no folding", {"WN_FOLD_BUDGET": "0"}),
 ]
 ctx = wn.Context(0)
 ctx.use_torch_stream()
@@ -56,7 +57,7 @@ for name, env in VARIANTS:
     # a strided sample of the volume, kept for the bitwise comparison between variants with the same fold set
     sample = out[:: max(1, nz // 64), ::16, :].clone()
     same = ""
-    key = env.get("WN_FOLD_BUDGET")
+    key = env.get("WN_FOLD_BUDGET", "default")
     if key in keep:
         same = "  bitwise == first variant with this budget: %s" % bool(torch.equal(sample, keep[key]))
     else:

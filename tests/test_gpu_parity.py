@@ -316,7 +316,10 @@ def test_folding_non_pow2_tile_and_periods(wn, oracle):
     w = wn.WaveletNoise(30, 807)
     w.generateNoiseTile3D()
     rng = float(tile.max() - tile.min())
-    for nx, ny, nz in ((240, 120, 64), (242, 61, 33)):            # second shape: nx % 4 != 0 -> one-sample-per-lane kernel
+    # (242, 61, 33): nx % 4 != 0 -> one-sample-per-lane kernel; (244, 61, 75) and (128, 40, 130): partial x / y / z
+    # bricks of the z-streaming kernel, period blocks that wrap inside a brick (periods 15 / 30 / 60 are not
+    # multiples of its 32-sample z extent)
+    for nx, ny, nz in ((240, 120, 64), (242, 61, 33), (244, 61, 75), (128, 40, 130)):
         xs = np.arange(nx, dtype=np.float32) * np.float32(0.5)
         ys = np.arange(ny, dtype=np.float32) * np.float32(0.5) + np.float32(3.25)
         zs = np.arange(nz, dtype=np.float32) * np.float32(0.5) - np.float32(7.0)

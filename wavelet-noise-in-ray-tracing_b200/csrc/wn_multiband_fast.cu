@@ -25,6 +25,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -582,7 +585,14 @@ k_mb3d_col4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int
     // per-thread ring of RING float4 slots in shared memory filled by cp.async: the first RING-1 planes are requested
     // here, before the tables and the X pass, and plane k+RING-1 is requested when plane k is consumed, so the loads
     // have the whole prologue and RING-1 z steps to land and cost no registers.
+    // RING < 0: the same look-ahead in registers instead (PF = -RING planes, plain loads): fewer LSU wavefronts per
+    // sample, 4 registers per plane.
+    constexpr int PF = RING < 0 ? -RING : 0;
+    static_assert(RING != 0 && (PF == 0 || BZ % PF == 0), "look-ahead depth");
     float4 *ring = reinterpret_cast<float4 *>(s_rowoff + max_rows) + threadIdx.x;
+    float4 pq[PF > 0 ? PF : 1];
+#pragma unroll
+    for (int d = 0; d < (PF > 0 ? PF : 1); ++d) pq[d] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     const size_t pplane = (size_t)fold.Lx * fold.Ly;
     const float *pcol = nullptr, *pp = nullptr;
     int kk = 0;
@@ -594,13 +604,23 @@ k_mb3d_col4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int
         kk = fold.kphase + k0;
         if (kk >= fold.Lz) kk %= fold.Lz;
         pp = pcol + kk * pplane;
+        if constexpr (RING > 0) {
 #pragma unroll
-        for (int d = 0; d < RING - 1; ++d) {
-            if (d < kmax) {
-                cp_async16(ring + d * NT, pp);
-                if (++kk == fold.Lz) { kk = 0; pp = pcol; } else pp += pplane;
+            for (int d = 0; d < RING - 1; ++d) {
+                if (d < kmax) {
+                    cp_async16(ring + d * NT, pp);
+                    if (++kk == fold.Lz) { kk = 0; pp = pcol; } else pp += pplane;
+                }
+                cp_async_commit();
             }
-            cp_async_commit();
+        } else {
+#pragma unroll
+            for (int d = 0; d < PF; ++d) {
+                if (d < kmax) {
+                    pq[d] = __ldg(reinterpret_cast<const float4 *>(pp));
+                    if (++kk == fold.Lz) { kk = 0; pp = pcol; } else pp += pplane;
+                }
+            }
         }
     }
 
@@ -634,8 +654,8 @@ k_mb3d_col4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int
 
     const size_t plane = (size_t)nx * ny;
     float *o = out + ((size_t)i + (size_t)nx * j + plane * k0);
-#pragma unroll 4
-    for (int k = 0; k < kmax; ++k) {
+    // one z step: the bands' contributions to sample plane k
+    auto zstep = [&](int k) {
         float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -650,18 +670,45 @@ k_mb3d_col4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int
             }
             a = q4_zcontract(a, tz, v[b]);
         }
-        if (folded) {
-            if (k + RING - 1 < kmax) {                         // slot of plane k-1, consumed in the previous step
-                cp_async16(ring + ((k + RING - 1) % RING) * NT, pp);
-                if (++kk == fold.Lz) { kk = 0; pp = pcol; } else pp += pplane;
+        return a;
+    };
+    if constexpr (RING > 0) {
+#pragma unroll 4
+        for (int k = 0; k < kmax; ++k) {
+            float4 a = zstep(k);
+            if (folded) {
+                if (k + RING - 1 < kmax) {                     // slot of plane k-1, consumed in the previous step
+                    cp_async16(ring + ((k + RING - 1) % RING) * NT, pp);
+                    if (++kk == fold.Lz) { kk = 0; pp = pcol; } else pp += pplane;
+                }
+                cp_async_commit();
+                cp_async_wait<RING - 1>();                     // plane k has landed
+                const float4 pv = ring[(k % RING) * NT];
+                a.x += pv.x; a.y += pv.y; a.z += pv.z; a.w += pv.w;
             }
-            cp_async_commit();
-            cp_async_wait<RING - 1>();                         // plane k has landed
-            const float4 pv = ring[(k % RING) * NT];
-            a.x += pv.x; a.y += pv.y; a.z += pv.z; a.w += pv.w;
+            __stcs(reinterpret_cast<float4 *>(o), a);
+            o += plane;
         }
-        __stcs(reinterpret_cast<float4 *>(o), a);
-        o += plane;
+    } else {
+        for (int kb = 0; kb < kmax; kb += PF) {
+#pragma unroll
+            for (int d = 0; d < PF; ++d) {
+                const int k = kb + d;
+                if (k < kmax) {
+                    float4 a = zstep(k);
+                    if (folded) {
+                        const float4 pv = pq[d];
+                        if (k + PF < kmax) {
+                            pq[d] = __ldg(reinterpret_cast<const float4 *>(pp));
+                            if (++kk == fold.Lz) { kk = 0; pp = pcol; } else pp += pplane;
+                        }
+                        a.x += pv.x; a.y += pv.y; a.z += pv.z; a.w += pv.w;
+                    }
+                    __stcs(reinterpret_cast<float4 *>(o), a);
+                    o += plane;
+                }
+            }
+        }
     }
 }
 
@@ -732,6 +779,8 @@ struct HostEntry {
     }
 };
 
+static_assert(sizeof(HostEntry) == 16, "HostEntry is compared with memcmp");
+
 struct HostAxes {
     int nb = 0, nx = 0, ny = 0, nz = 0;
     mutable int runs = 0;           // lattice kernels launched so far in this call (the first one follows k_axis_tables)
@@ -745,16 +794,26 @@ struct HostAxes {
     const int *fz(int row) const { return fy(row) + ny; }
 };
 
+// ceilf without the libm call (the table loops below are on the per-call host path): exact for |a| < 2^31, which
+// holds for every coordinate the int conversion in the reference (cpp:196) is defined for
+inline int ceil_to_int(float a)
+{
+    if (!(a > -2147483000.0f && a < 2147483000.0f)) return (int)std::ceil(a);
+    const int m = (int)a;                                      // truncates toward zero
+    return m + ((float)m < a ? 1 : 0);
+}
+
 inline void host_entry(float coord, float scale, int n, HostEntry &e, int &first)   // mirrors axis_entry()
 {
     const float a = coord * scale - 0.5f;
-    const int mid = (int)std::ceil(a);
+    const int mid = ceil_to_int(a);
     const float tt = (float)mid - a;
     e.w0 = tt * tt * 0.5f;
     const float s1 = 1.0f - tt;
     e.w2 = s1 * s1 * 0.5f;
     e.w1 = 1.0f - e.w0 - e.w2;
     first = mid - 1;
+    if ((n & (n - 1)) == 0) { e.cell = first & (n - 1); return; }
     const int m = first % n;
     e.cell = m < 0 ? m + n : m;
 }
@@ -800,6 +859,24 @@ BrickPlan plan_bricks(const HostAxes &h, const unsigned char *rows, int nb, int 
     return p;
 }
 
+// raises a kernel's dynamic shared memory limit when a launch needs more than it has been granted so far (48 KB by
+// default); remembered per kernel instantiation and device, so the driver call happens once, not per launch
+template <typename K>
+bool allow_smem(K kern, size_t smem)
+{
+    if (smem <= 48 * 1024) return true;
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> granted;     // (kernel, device ordinal) -> bytes
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &g = granted[std::make_pair(reinterpret_cast<const void *>(kern), dev)];
+    if (smem <= g) return true;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    g = smem;
+    return true;
+}
+
 // launch with the programmatic stream serialisation attribute (WN_PDL=0: plain stream order, for A/B runs)
 template <typename... KArgs, typename... Args>
 cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
@@ -821,8 +898,7 @@ int launch_brick(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
 {
     auto kern = t.pow2 ? k_mb3d_brick<BY, BZ, NT, true> : k_mb3d_brick<BY, BZ, NT, false>;
     const size_t smem = plan.smem;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (!allow_smem(kern, smem)) return -1;
     dim3 grid((nx + 31) / 32, (ny + BY - 1) / BY, (nk + BZ - 1) / BZ);
     launch_chained(kern, grid, dim3(NT), smem, st, t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, out);
     return 1;
@@ -834,8 +910,7 @@ int launch_brick4(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
 {
     auto kern = t.pow2 ? k_mb3d_brick4<BY, BZ, NT, true> : k_mb3d_brick4<BY, BZ, NT, false>;
     const size_t smem = plan.smem;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (!allow_smem(kern, smem)) return -1;
     dim3 grid((nx + 127) / 128, (ny + BY - 1) / BY, (nk + BZ - 1) / BZ);
     launch_chained(kern, grid, dim3(NT), smem, st, t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, out);
     return 1;
@@ -847,9 +922,8 @@ int launch_col4(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
 {
     constexpr int BY = 8, BZ = 32, NT = 256;
     auto kern = t.pow2 ? k_mb3d_col4<NB, BY, BZ, NT, RING, true> : k_mb3d_col4<NB, BY, BZ, NT, RING, false>;
-    const size_t smem = plan.smem + (fold.P ? (size_t)RING * NT * sizeof(float4) : 0);   // + the period-block ring
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    const size_t smem = plan.smem + (fold.P && RING > 0 ? (size_t)RING * NT * sizeof(float4) : 0);   // + the period-block ring
+    if (!allow_smem(kern, smem)) return -1;
     const int nyb = (ny + BY - 1) / BY, nzb = (nk + BZ - 1) / BZ;
     WnOrder ord{1, nyb, 1, nzb};
     // replica-first order when the period block cannot stay in L2 by itself (config 3, 512 MiB block: 1.08 vs 1.17 ms
@@ -902,14 +976,16 @@ int brick_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsign
     if (pick < 0 && can4 && col4_on && b.nbands >= 1 && b.nbands <= 2 && (ny + 7) / 8 <= 65535 && (nk + 31) / 32 <= 65535) {
         plan = plan_bricks(h, rows, b.nbands, ny, k0, nk, 8, 32, 128, true);
         if (plan.ok && plan.smem <= 56 * 1024) {
-            // ring of 8 period-block planes per thread (32 KB) while four CTAs still fit an SM, else 4 planes
+            // ring of 8 period-block planes per thread (32 KB) while four CTAs still fit an SM, else 4 planes;
+            // WN_RING=-2/-4: register look-ahead instead (A/B runs)
             int ring = plan.smem <= 24 * 1024 ? 8 : 4;
-            if (const char *e = getenv("WN_RING")) ring = atoi(e) == 4 ? 4 : 8;
-            if (b.nbands == 1)
-                return ring == 8 ? launch_col4<1, 8>(t, tabs, nx, ny, nk, out, plan, fold, st)
-                                 : launch_col4<1, 4>(t, tabs, nx, ny, nk, out, plan, fold, st);
-            return ring == 8 ? launch_col4<2, 8>(t, tabs, nx, ny, nk, out, plan, fold, st)
-                             : launch_col4<2, 4>(t, tabs, nx, ny, nk, out, plan, fold, st);
+            if (const char *e = getenv("WN_RING")) ring = atoi(e);
+#define WN_COL4_CASE(nb, rg) if (b.nbands == nb && ring == rg) return launch_col4<nb, rg>(t, tabs, nx, ny, nk, out, plan, fold, st);
+            WN_COL4_CASE(1, 8) WN_COL4_CASE(1, 4) WN_COL4_CASE(1, -2) WN_COL4_CASE(1, -4)
+            WN_COL4_CASE(2, 8) WN_COL4_CASE(2, 4) WN_COL4_CASE(2, -2) WN_COL4_CASE(2, -4)
+#undef WN_COL4_CASE
+            return b.nbands == 1 ? launch_col4<1, 8>(t, tabs, nx, ny, nk, out, plan, fold, st)
+                                 : launch_col4<2, 8>(t, tabs, nx, ny, nk, out, plan, fold, st);
         }
     }
     if (pick >= kFirstShape4 && !can4) pick = -1;
@@ -963,9 +1039,7 @@ int axis_period(const HostEntry *e, int len)
     if (len < 4) return len;
     for (int P = 1; P <= len / 2; ++P) {
         if (!(e[P] == e[0])) continue;
-        bool ok = true;
-        for (int i = 0; i + P < len && ok; ++i) ok = e[i + P] == e[i];
-        if (ok) return P;
+        if (std::memcmp(e + P, e, (size_t)(len - P) * sizeof(HostEntry)) == 0) return P;   // entries are 16 packed bytes
     }
     return len;
 }

@@ -55,6 +55,27 @@ def dist_info():
     return 0, 1, False
 
 
+def bind_to_gpu_numa(device_index):
+    """Restrict this process to the CPUs NVML reports as local to CUDA device `device_index`, so host staging buffers
+    allocated afterwards (pinned output arrays) land on the NUMA node next to that GPU's PCIe root.  With one process
+    per GPU and no binding, every rank's buffers end up on the launcher's node and half of the GPUs copy across the
+    socket interconnect.  Returns the previous affinity set (pass it to os.sched_setaffinity(0, ...) to undo), or None
+    when NVML / the device is unavailable (nothing changed)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return prev
+    except Exception:                                        # noqa: BLE001  (best effort: placement only)
+        return None
+
+
 def broadcast_tile(buffer, src=0):
     """Replicate the tile: `buffer` is a torch tensor (CUDA view of the tile for NCCL, CPU tensor for gloo)
     holding the coefficients on `src` and uninitialised storage elsewhere."""
