@@ -6,8 +6,8 @@
 //   reject while r2 > 1 or r2 == 0;  m = sqrt(-2*log(r2)/r2);  return y*m, then x*m on the next call.
 // The sequence looks serial but is not: attempts are aligned to even draw indices, every accept/reject decision
 // is independent, and the output slot of an accepted attempt is 2 * (number of accepted attempts before it).
-//   k_mt19937      one CTA regenerates the 624-word state block after block (three dependent sub-steps per
-//                  block, ping-pong buffers in shared memory) and streams the tempered words to global memory;
+//   k_mt19937      one CTA extends the MT recurrence 224 elements per step in a circular shared-memory buffer
+//                  while a second thread group tempers and streams the previous step's words to global memory;
 //   k_polar_count  accept flags per attempt -> per-block accept counts;
 //   k_scan_blocks  exclusive scan of the block counts (single CTA);
 //   k_polar_emit   re-evaluates the flags, ranks them (ballot/popc + block offset) and writes y*m, x*m.
@@ -36,33 +36,40 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
     return y;
 }
 
-// draws[0 .. nblocks*624): the first nblocks*624 outputs of std::mt19937(seed)
-__global__ void __launch_bounds__(256) k_mt19937(uint32_t seed, uint32_t *__restrict__ draws, int nblocks)
+// draws[0 .. nblocks*624): the first nblocks*624 outputs of std::mt19937(seed).
+// The generator is the linear recurrence x[p] = x[p-227] ^ twist(x[p-624], x[p-623]) over the seed expansion
+// x[0..623], output q = temper(x[624+q]).  The shortest dependency is 227 elements, so 224 consecutive elements
+// (7 warps) are independent: one step = 224 threads extend the sequence in a 2048-word circular buffer in shared
+// memory while 224 other threads temper and store the elements of the PREVIOUS step, one barrier per step.  The chain
+// of n^3 * 1.3 / 224 dependent steps is what bounds the kernel (latency, one CTA), not bandwidth.
+constexpr int MT_STEP = 224, MT_RING = 2048;
+
+__global__ void __launch_bounds__(512) k_mt19937(uint32_t seed, uint32_t *__restrict__ draws, int nblocks)
 {
-    __shared__ uint32_t s[2][MT_N];
+    __shared__ uint32_t x[MT_RING];
     const int t = threadIdx.x;
     if (t == 0) {
         uint32_t v = seed;
-        s[0][0] = v;
-        for (int i = 1; i < MT_N; ++i) { v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i; s[0][i] = v; }
+        x[0] = v;
+        for (int i = 1; i < MT_N; ++i) { v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i; x[i] = v; }
     }
     __syncthreads();
-    int cur = 0;
-    for (int blk = 0; blk < nblocks; ++blk) {
-        const uint32_t *o = s[cur];
-        uint32_t *nw = s[cur ^ 1];
-        if (t < 227) nw[t] = mt_twist(o[t], o[t + 1], o[t + MT_M]);                       // k = 0..226: old operands only
-        __syncthreads();
-        if (t < 227) { const int k = 227 + t; nw[k] = mt_twist(o[k], o[k + 1], nw[k - 227]); }   // k = 227..453
-        __syncthreads();
-        if (t < 170) {                                                                    // k = 454..623
-            const int k = 454 + t;
-            nw[k] = mt_twist(o[k], k == MT_N - 1 ? nw[0] : o[k + 1], nw[k - 227]);
+    const long long end = (long long)MT_N * nblocks + MT_N;     // one past the last sequence element needed
+    const bool producer = t < MT_STEP;
+    const int u = t - 256;                                      // consumer lane 0..223 (threads 256..479)
+    for (long long p0 = MT_N; p0 < end + MT_STEP; p0 += MT_STEP) {
+        if (producer) {
+            const long long p = p0 + t;
+            if (p < end) {
+                const unsigned i = (unsigned)p;
+                x[i & (MT_RING - 1)] = mt_twist(x[(i - MT_N) & (MT_RING - 1)], x[(i - MT_N + 1) & (MT_RING - 1)],
+                                                x[(i - (unsigned)(MT_N - MT_M)) & (MT_RING - 1)]);
+            }
+        } else if (u >= 0 && u < MT_STEP) {
+            const long long q = p0 - MT_STEP + u;               // written by the previous step
+            if (q >= MT_N && q < end) draws[q - MT_N] = mt_temper(x[(unsigned)q & (MT_RING - 1)]);
         }
         __syncthreads();
-        uint32_t *out = draws + (size_t)blk * MT_N;
-        for (int i = t; i < MT_N; i += 256) out[i] = mt_temper(nw[i]);
-        cur ^= 1;
     }
 }
 
@@ -208,7 +215,7 @@ int wn_launch_gaussian_fill(unsigned seed, float *out, size_t count, unsigned lo
     const size_t nb = (attempts + PB - 1) / PB;
     if (cudaMallocAsync(&draws, nblocks * MT_N * sizeof(uint32_t), st) != cudaSuccess) return -1;
     if (cudaMallocAsync(&bc, nb * sizeof(uint32_t), st) != cudaSuccess) { cudaFreeAsync(draws, st); return -1; }
-    k_mt19937<<<1, 256, 0, st>>>(seed, draws, (int)nblocks);
+    k_mt19937<<<1, 512, 0, st>>>(seed, draws, (int)nblocks);
     k_polar_count<<<(unsigned)nb, PB, 0, st>>>(draws, attempts, bc);
     k_scan_blocks<<<1, 1024, 0, st>>>(bc, (int)nb, accepted);
     k_polar_emit<<<(unsigned)nb, PB, 0, st>>>(draws, attempts, bc, out, count, accepted);
