@@ -94,6 +94,7 @@ int  wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const fl
 int  wn_mb3d_fast_run(WnTileView t, WnLattice c, const float *h_ys, const float *h_zs, const WnBands &all_bands,
                       const unsigned char *all_rows, const WnFastPlan *plan, int k0, int nk, float *out, cudaStream_t st);
 void wn_mb3d_fast_finish(WnFastPlan *plan, cudaStream_t st);
+void wn_mb3d_fast_detach(WnFastPlan *plan, void **tab, void **P);
 
 // 3D tile -> x-padded replica (row pitch n+WN_TILE_PAD, the extra cells wrap around)
 int wn_launch_pad_tile(const float *N, float *Npad, int n, cudaStream_t st);

@@ -1196,6 +1196,19 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
     return launched + r + r2;
 }
 
+// finish without releasing the device scratch: hands the axis tables and the period block to the caller, which frees
+// them (cudaFreeAsync) once the kernels that read them are known to be complete
+void wn_mb3d_fast_detach(WnFastPlan *plan, void **tab, void **P)
+{
+    *tab = plan->owns_tab ? plan->tab : nullptr;
+    *P = plan->P;
+    if (plan->owns_tab) delete static_cast<HostAxes *>(plan->host_axes);
+    plan->P = nullptr;
+    plan->tab = nullptr;
+    plan->host_axes = nullptr;
+    plan->owns_tab = 0;
+}
+
 void wn_mb3d_fast_finish(WnFastPlan *plan, cudaStream_t st)
 {
     if (plan->P) cudaFreeAsync(plan->P, st);
