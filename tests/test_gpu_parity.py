@@ -371,6 +371,38 @@ def test_block_cyclic_shards_reassemble(wn, gpu_tiles, tiles128):
     assert np.abs(got[idx] - exact).max() <= tol
 
 
+def test_back_to_back_device_calls_with_tile_rebuilds(wn):
+    """Consecutive device-resident FAST calls without any synchronisation in between (the period-block chain of call
+    i+1 runs on the side stream while call i's main kernel is still in flight), with different lattices and the tile
+    rebuilt between some of them.  Every result must equal the exact kernel evaluated afterwards, call by call, on a
+    second object that replays the same tile sequence."""
+    import torch
+    ctx = wn.Context(0)
+    ctx.use_torch_stream()
+    w = wn.WaveletNoise(32, 77, ctx)
+    w.generateNoiseTile3D()
+    bs, wts = np.array([1.0, 2.0, 4.0, 8.0], np.float32), np.array([1.0, 0.5, 0.25, 0.125], np.float32)
+    shapes = [(256, 64, 96), (128, 128, 64), (256, 64, 96), (192, 40, 70), (128, 128, 64), (256, 64, 96), (64, 64, 32)]
+    rebuild_before = {2, 3, 6}
+    axes = lambda n, off: (np.arange(n, dtype=np.float32) + np.float32(off)) * np.float32(0.125)      # noqa: E731
+    outs = []
+    for it, (nx, ny, nz) in enumerate(shapes):
+        if it in rebuild_before:
+            w.generateNoiseTile3D()                          # continues the member RNG stream: a different tile
+        outs.append(w.multiband3D_lattice(axes(nx, 0), axes(ny, 3), axes(nz, it), bs, wts, 0.9, device_out=True))
+    torch.cuda.synchronize()
+    ref = wn.WaveletNoise(32, 77, ctx)
+    ref.generateNoiseTile3D()
+    for it, (nx, ny, nz) in enumerate(shapes):
+        if it in rebuild_before:
+            ref.generateNoiseTile3D()
+        tile = np.asarray(ref.getNoiseCoefficients())
+        want = ref.multiband3D_lattice(axes(nx, 0), axes(ny, 3), axes(nz, it), bs, wts, 0.9, mode=wn.WN_EVAL_EXACT)
+        tol = 1e-5 * float(tile.max() - tile.min()) * float(wts.sum()) * 0.9
+        assert np.abs(outs[it].cpu().numpy() - want).max() <= tol, it
+    ctx.set_stream(None)
+
+
 def test_argument_errors(wn, gpu_tiles):
     t3 = gpu_tiles[3]
     ax = lattice_axis(np.arange(8))
