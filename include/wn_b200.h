@@ -151,6 +151,17 @@ int  wn_multiband3d_points(const wn_tile *tile, const float *p, size_t count,
  * bit-identical to the CPU loop.  replaces the per-pixel loops experient/main.cpp:18-30, :45-58. */
 int  wn_eval2d_lattice(const wn_tile *tile, const float *xs, int nx, const float *ys, int ny,
                        float pre_scale, float post_scale, float *out, int space);
+/* wn_multiband3d_lattice: out[i + nx*(j + ny*k)] = post_scale * sum_b weights[b] * evaluate3D(p_ijk * band_scale[b])
+ * (the composition of wn_multiband3d_points on a lattice; the axes are always HOST arrays).
+ * mode WN_EVAL_FAST: separable evaluation; bands whose samples repeat with the tile period on this lattice are
+ *   evaluated once per period ("folded") in stream-ordered scratch memory (up to 512 MiB per nesting level, released
+ *   after the call; device-output calls of <= 2^29 samples keep two generations of it between calls).  Results are
+ *   within 1e-5 * (tile max - tile min) per unit of band weight of the reference and do not depend on how the call is
+ *   chunked; calls on different lattices (a slab vs the whole volume) may differ in the last bit.
+ * mode WN_EVAL_EXACT: reference operation order, bit-identical to the CPU loop.
+ * space WN_DEVICE: the call only enqueues.  `out` is ready in the order of the context's compute stream
+ *   (wn_ctx_set_stream); the library may run the part of the work that does not depend on earlier work of that stream
+ *   on an internal stream, which the compute stream then waits for. */
 int  wn_multiband3d_lattice(const wn_tile *tile,
                             const float *xs, int nx, const float *ys, int ny, const float *zs, int nz,
                             const float *band_scale, const float *weights, int nbands,

@@ -5,20 +5,27 @@
 // band; composition per Cook & DeRose App. 2).  This file may reorder the 27-tap sum (separable form) and use
 // FMAs; tests bound the difference to the CPU reference by 1e-5 * (tile max - tile min).
 //
-// Design (k_mb3d_brick).  On an axis-aligned lattice the quadratic B-spline weights factor per axis, so the
-// 27-tap gather is a tensor-product resampling  out = (Wz (x) Wy (x) Wx) N  with 3 non-zeros per row.
-//   * k_axis_tables turns every axis coordinate of every band into {w0,w1,w2, first tap cell} once per launch
-//     (un-fused arithmetic, so the tap cells are the reference's integers exactly).
-//   * one CTA owns a brick of 32 x BY x BZ samples and loops over the bands.  Per band:
-//       X pass : every tile row (cy,cz) the brick touches is contracted along x for the CTA's 32 x-samples
-//                (lane = x sample; 3 read-only loads of the L2-resident tile, 3 FMA) into shared memory U[cz][cy][32].
-//       YZ pass: thread (lane, j) walks its z column with a 3-deep sliding register window of y-contracted
-//                values V[cz] = sum_f wy[f] U[cz][cy_j+f][lane]; each sample is 3 FMAs of the window with the
-//                z weights (band weight and post scale folded in).  The window only advances when the next
-//                sample's first tap cell advances, so low bands (many samples per cell) cost ~3 FMA per sample.
-//     Shared-memory traffic is conflict-free (lane = fastest index), stores are 128 B per warp instruction.
-//   * requirements: y and z tap cells non-decreasing along the axis and U fitting in shared memory; anything else
-//     (unsorted axes, huge steps) runs k_mb3d_gather, the plain one-sample-per-thread form.
+// Design.  On an axis-aligned lattice the quadratic B-spline weights factor per axis, so the 27-tap gather is a
+// tensor-product resampling  out = (Wz (x) Wy (x) Wx) N  with 3 non-zeros per row.
+//   * k_axis_tables turns every axis coordinate of every band into {w0,w1,w2, first tap cell} once per call
+//     (un-fused arithmetic, so the tap cells are the reference's integers exactly); the host builds the same table
+//     (HostAxes) for period detection and shared-memory planning.
+//   * Periodic folding (wn_mb3d_fast_prepare): a band whose table entries repeat with period P along every axis is
+//     evaluated once on its period block and added by index mod period; blocks nest.  See the comment there.
+//   * Brick kernels.  A CTA owns a brick of samples and works per band in two passes:
+//       X pass : every tile row (cy,cz) the brick touches is contracted along x for the CTA's x-samples (read-only
+//                loads of the L2-resident, x-padded tile) into shared memory U[cz][cy][x];
+//       YZ pass: a thread walks its z column with a 3-deep sliding register window of y-contracted values
+//                V[cz] = sum_f wy[f] U[cz][cy+f][x]; each sample is 3 FMAs of the window with the z weights (band weight
+//                and post scale folded in).  The window only advances when the next sample's first tap cell advances,
+//                so low bands (many samples per cell) cost ~3 FMA per sample.
+//     k_mb3d_col4  : 128 x 8 x 32 samples, four x-samples per lane, band loop INSIDE the z loop (one or two bands
+//                    left after folding); the period-block column streams through a cp.async ring.  Main kernel.
+//     k_mb3d_brick4: 128 x BY x BZ samples, four x-samples per lane, all bands resident, BZ accumulators per thread.
+//     k_mb3d_brick : 32 x BY x BZ samples, one x-sample per lane, per-band phases (large footprints).
+//     k_mb3d_gather: one sample per thread, for lattices that do not qualify (unsorted y/z axes, huge steps).
+//     All four produce bit-identical samples (same per-sample operation order).
+//   * The launches of a call are chained with programmatic dependent launch (chain_wait / chain_release).
 #include "wn_internal.h"
 
 #include <algorithm>
