@@ -1182,7 +1182,10 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
         ++dst.nbands;
     }
     float *P = nullptr;
-    if (cudaMallocAsync(&P, (size_t)(Lx * Ly * Lz) * sizeof(float), st) != cudaSuccess) return -1;
+    if (cudaMallocAsync(&P, (size_t)(Lx * Ly * Lz) * sizeof(float), st) != cudaSuccess) {
+        cudaGetLastError();                                    // no scratch for the block: evaluate every band per sample
+        return launched;
+    }
     // The period block is itself a lattice, and the folded bands with the shortest periods repeat inside it: evaluate
     // it with the same machinery (nested folding), e.g. bands 7, 8 of config 3 on 128^3 inside band 6's 256^3 block.
     const WnLattice lc{c.xs, c.ys, c.zs, (int)Lx, (int)Ly, (int)Lz};
