@@ -117,6 +117,10 @@ __device__ float eval3d_projected(const WnTileView &t, const float p[3], const f
     const float b0 = 1.0f - 0.5f * nrm[0] * nrm[0];           // -d t_0 / d D_0  (in [0.5, 1])
     const float b1 = 0.5f * nrm[0] * nrm[1];                   //  d t_1 / d D_0
     const float b2 = 0.5f * nrm[0] * nrm[2];                   //  d t_2 / d D_0
+    // the bounds are only a conservative filter (eps absorbs a few ulp), so reciprocals replace the five divisions
+    // per row: about 40 instructions less per row of the bounding box
+    const bool use1 = fabsf(b1) > 1e-6f, use2 = fabsf(b2) > 1e-6f;
+    const float ib0 = 1.0f / b0, ib1 = use1 ? 1.0f / b1 : 0.0f, ib2 = use2 ? 1.0f / b2 : 0.0f;
     float result = 0.0f;
     for (int c2 = lo[2]; c2 <= hi[2]; ++c2) {
         const float f2 = (float)c2;
@@ -131,21 +135,21 @@ __device__ float eval3d_projected(const WnTileView &t, const float p[3], const f
             float dlo = -1e30f, dhi = 1e30f;
             {   // t_0 = (1.5 + n0 K/2) - b0 D0 in (-eps, 3+eps)
                 const float a = 1.5f + 0.5f * nrm[0] * K;
-                dlo = fmaxf(dlo, (a - 3.0f - eps) / b0);
-                dhi = fminf(dhi, (a + eps) / b0);
+                dlo = fmaxf(dlo, (a - 3.0f - eps) * ib0);
+                dhi = fminf(dhi, (a + eps) * ib0);
             }
             bool row_empty = false;
             {   // t_1 = (1.5 - D1 + n1 K/2) + b1 D0
                 const float a = 1.5f - D1 + 0.5f * nrm[1] * K;
-                if (fabsf(b1) > 1e-6f) {
-                    const float x0 = (-eps - a) / b1, x1 = (3.0f + eps - a) / b1;
+                if (use1) {
+                    const float x0 = (-eps - a) * ib1, x1 = (3.0f + eps - a) * ib1;
                     dlo = fmaxf(dlo, fminf(x0, x1)); dhi = fminf(dhi, fmaxf(x0, x1));
                 } else if (a <= -eps - 8.0f * fabsf(b1) || a >= 3.0f + eps + 8.0f * fabsf(b1)) row_empty = true;
             }
             {   // t_2 = (1.5 - D2 + n2 K/2) + b2 D0
                 const float a = 1.5f - D2 + 0.5f * nrm[2] * K;
-                if (fabsf(b2) > 1e-6f) {
-                    const float x0 = (-eps - a) / b2, x1 = (3.0f + eps - a) / b2;
+                if (use2) {
+                    const float x0 = (-eps - a) * ib2, x1 = (3.0f + eps - a) * ib2;
                     dlo = fmaxf(dlo, fminf(x0, x1)); dhi = fminf(dhi, fmaxf(x0, x1));
                 } else if (a <= -eps - 8.0f * fabsf(b2) || a >= 3.0f + eps + 8.0f * fabsf(b2)) row_empty = true;
             }
