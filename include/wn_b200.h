@@ -156,8 +156,9 @@ int  wn_eval2d_lattice(const wn_tile *tile, const float *xs, int nx, const float
  * mode WN_EVAL_FAST: separable evaluation; bands whose samples repeat with the tile period on this lattice are
  *   evaluated once per period ("folded") in stream-ordered scratch memory (up to 512 MiB per nesting level, released
  *   after the call; device-output calls of <= 2^29 samples keep two generations of it between calls).  Results are
- *   within 1e-5 * (tile max - tile min) per unit of band weight of the reference and do not depend on how the call is
- *   chunked; calls on different lattices (a slab vs the whole volume) may differ in the last bit.
+ *   within 1e-5 * (tile max - tile min) per unit of band weight of the reference, and a sample's value depends only on
+ *   its coordinates, the bands and the tile: not on folding, chunking, the band order given, or how a volume is cut
+ *   into calls (slabs / shards are bit-identical to the single call).
  * mode WN_EVAL_EXACT: reference operation order, bit-identical to the CPU loop.
  * space WN_DEVICE: the call only enqueues.  `out` is ready in the order of the context's compute stream
  *   (wn_ctx_set_stream); the library may run the part of the work that does not depend on earlier work of that stream

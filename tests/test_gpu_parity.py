@@ -331,44 +331,62 @@ def test_folding_non_pow2_tile_and_periods(wn, oracle):
         assert_bits(exact, want, "exact lattice n=30")
 
 
-def test_sharded_slabs_reassemble(wn, gpu_tiles, tiles128):
-    """Config 3 contiguous z-slab sharding: the slabs 1/2/4/8 ranks would compute, each with its own call.  The set of
-    bands a call folds depends on its own lattice (a short slab has fewer whole z periods), so the summation order of
-    a sample can differ between the slab call and the single call: equal within the FAST tolerance, not bitwise."""
+def test_sharded_slabs_reassemble_bit_exactly(wn, gpu_tiles):
+    """Config 3 contiguous z-slab sharding: the slabs 1/2/4/8 ranks would compute, each with its own call.  A call folds
+    the bands that repeat on ITS lattice (a short slab has fewer whole z periods than the volume), but a sample is
+    always summed in the canonical band order, so the slabs are bit-identical to the single call."""
     sh = wnpkg.load_sub("sharding")
     t = gpu_tiles[3]
     ax = lattice_axis(np.arange(1024))
     zs = ax[:512:2]                                                # 256 slices, still commensurate with the tile
     full = t.multiband3D_lattice(ax[:256], ax[:256], zs, BANDS, WEIGHTS, float(POST))
-    tol = 1e-5 * float(tiles128[3].max() - tiles128[3].min()) * float(WEIGHTS.sum()) * float(POST)
     for world in (2, 4, 8):
         parts = []
         for r in range(world):
             b, e = sh.slab_range(zs.size, r, world)
             parts.append(t.multiband3D_lattice(ax[:256], ax[:256], zs[b:e], BANDS, WEIGHTS, float(POST)))
-        assert np.abs(np.concatenate(parts, 0) - full).max() <= tol, world
+        assert_bits(np.concatenate(parts, 0), full, f"{world} slabs")
 
 
-def test_block_cyclic_shards_reassemble(wn, gpu_tiles, tiles128):
+def test_block_cyclic_shards_reassemble_bit_exactly(wn, gpu_tiles, tiles128):
     """Config 3 block-cyclic z sharding (what bench.py runs at N > 1): every rank evaluates the 32-slice chunks dealt to
-    it as one lattice call on its own, non-uniform z axis.  Ranks may fold different band sets than the single call,
-    so the reassembled volume is compared within the FAST tolerance, and against the exact kernel on one chunk."""
+    it as one lattice call on its own, non-uniform z axis.  1-GPU and N-GPU volumes are bit-identical (canonical
+    summation), and one chunk is checked against the exact kernel."""
     sh = wnpkg.load_sub("sharding")
     t = gpu_tiles[3]
     ax = lattice_axis(np.arange(1024))
     xs = ax[:256]
     full = t.multiband3D_lattice(xs, xs, ax, BANDS, WEIGHTS, float(POST))
-    rng = float(tiles128[3].max() - tiles128[3].min())
-    tol = 1e-5 * rng * float(WEIGHTS.sum()) * float(POST)
     for world in (2, 8):
         got = np.empty_like(full)
         for r in range(world):
             idx = sh.cyclic_slab_indices(ax.size, r, world)
             got[idx] = t.multiband3D_lattice(xs, xs, ax[idx], BANDS, WEIGHTS, float(POST))
-        assert np.abs(got - full).max() <= tol, world
+        assert_bits(got, full, f"{world} block-cyclic shards")
     idx = sh.cyclic_slab_indices(ax.size, 5, 8)[:32]
     exact = t.multiband3D_lattice(xs, xs, ax[idx], BANDS, WEIGHTS, float(POST), mode=wn.WN_EVAL_EXACT)
-    assert np.abs(got[idx] - exact).max() <= tol
+    tol = 1e-5 * float(tiles128[3].max() - tiles128[3].min()) * float(WEIGHTS.sum()) * float(POST)
+    assert np.abs(full[idx] - exact).max() <= tol
+
+
+def test_fast_result_does_not_depend_on_folding_or_kernel(wn, gpu_tiles, monkeypatch):
+    """The same lattice evaluated with every band per sample (no folding), with a small fold budget, with the default
+    one, with the brick4 main kernel and with unsorted band order: bit-identical (canonical summation order)."""
+    t = gpu_tiles[3]
+    ax = lattice_axis(np.arange(1024))
+    xs, ys, zs = ax[:256], ax[:128], ax[:192]
+    base = t.multiband3D_lattice(xs, ys, zs, BANDS, WEIGHTS, float(POST))
+    for env in ({"WN_FOLD_BUDGET": "0"}, {"WN_FOLD_BUDGET": str(1 << 20)}, {"WN_COL4": "0"}, {"WN_FOLD_NEST": "0"},
+                {"WN_BRICK": "4"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got = t.multiband3D_lattice(xs, ys, zs, BANDS, WEIGHTS, float(POST))
+        for k in env:
+            monkeypatch.delenv(k)
+        assert_bits(got, base, str(env))
+    perm = [3, 0, 4, 2, 1]
+    got = t.multiband3D_lattice(xs, ys, zs, BANDS[perm], WEIGHTS[perm], float(POST))
+    assert_bits(got, base, "band order")
 
 
 def test_back_to_back_device_calls_with_tile_rebuilds(wn):

@@ -72,6 +72,17 @@ __host__ __device__ __forceinline__ int tabs_row(const WnTabs &t, int b) { retur
 __device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void chain_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Canonical summation.  The bands of a call are ordered by ascending scale (ties: band index), c0 < c1 < ... < ck, and a
+// sample is ALWAYS formed as  B_c0 + (B_c1 + (... + (B_ck + 0)))  where each band value B is computed from zero by
+// band_value().  Folded bands are a suffix of that order and their period block holds the canonical sum of the suffix, so
+// a kernel starts from the period-block value (or 0) and adds its own bands from the highest scale down.  The result
+// of a sample therefore does not depend on which bands were folded, how period blocks nest, which kernel ran, or how
+// the lattice was partitioned into calls: shards, chunks and the single call are bit-identical.
+__device__ __forceinline__ float band_value(const float4 tz, float v0, float v1, float v2)
+{
+    return fmaf(tz.x, v0, fmaf(tz.y, v1, __fmul_rn(tz.z, v2)));
+}
+
 inline WnFold make_fold(const float *P, int Lx, int Ly, int Lz, int kphase)
 {
     WnFold f{P, Lx, Ly, Lz, kphase, -1, -1};
@@ -142,7 +153,7 @@ k_mb3d_brick(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, in
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = blockIdx.x * 32, j0 = blockIdx.y * BY, k0 = blockIdx.z * BZ;
     const int pitch = n + WN_TILE_PAD;
-    if (tabs.wait_first) { chain_wait(); chain_release(); }
+    if (tabs.wait_first || fold.P) { chain_wait(); chain_release(); }   // tables / period block of the previous kernel
 
     // ---- phase 0: every table entry of every band in one round of independent loads (64 threads per band)
     {
@@ -160,13 +171,34 @@ k_mb3d_brick(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, in
     }
     __syncthreads();
 
+    // ---- running sums start from the period-block value (canonical summation: folded bands first)
+    const int i = i0 + lane;
+    const size_t plane = (size_t)nx * ny;
     float acc[C][BZ];
 #pragma unroll
     for (int c = 0; c < C; ++c)
 #pragma unroll
         for (int k = 0; k < BZ; ++k) acc[c][k] = 0.0f;
+    if (fold.P) {
+        const unsigned pplane = (unsigned)(fold.Lx * fold.Ly);
+        const int ic = min(i, nx - 1);
+        const unsigned pi = (unsigned)(fold.xmask >= 0 ? (ic & fold.xmask) : ic % fold.Lx);
+        int kz = fold.kphase + k0;
+        if (kz >= fold.Lz) kz %= fold.Lz;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = min(j0 + warp + c * NW, ny - 1);
+            const unsigned pj = pi + (unsigned)(fold.ymask >= 0 ? (j & fold.ymask) : j % fold.Ly) * (unsigned)fold.Lx;
+            int kk = kz;
+#pragma unroll
+            for (int k = 0; k < BZ; ++k) {
+                acc[c][k] = __ldg(fold.P + (pj + (unsigned)kk * pplane));
+                if (++kk == fold.Lz) kk = 0;
+            }
+        }
+    }
 
-    for (int b = 0; b < nbands; ++b) {
+    for (int b = nbands - 1; b >= 0; --b) {                    // highest scale first
         const float4 *tX = s_tab + b * PER_BAND, *tY = tX + 32, *tZ = tY + BY;
         // clamped entries repeat the last valid one, so the last entry carries the brick's last tap cell
         const int my0 = __float_as_int(tY[0].w), mz0 = __float_as_int(tZ[0].w);
@@ -238,45 +270,19 @@ k_mb3d_brick(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, in
                 }
 #pragma unroll
                 for (int c = 0; c < C; ++c)
-                    acc[c][k] = fmaf(tz.x, v[c][0], fmaf(tz.y, v[c][1], fmaf(tz.z, v[c][2], acc[c][k])));
+                    acc[c][k] = __fadd_rn(band_value(tz, v[c][0], v[c][1], v[c][2]), acc[c][k]);
             }
         }
-        if (b + 1 < nbands) __syncthreads();
+        if (b > 0) __syncthreads();
     }
 
-    if (!tabs.wait_first) { chain_wait(); chain_release(); }   // the period block is the previous kernel's output
-    const int i = i0 + lane;
+    if (!(tabs.wait_first || fold.P)) { chain_wait(); chain_release(); }   // nothing was read from the previous kernel so far
     if (i < nx) {
-        const size_t plane = (size_t)nx * ny;
-        // periodic bands were evaluated once on their period block (see wn_mb3d_fast_prepare): add them by index mod period
-        const unsigned pplane = (unsigned)(fold.Lx * fold.Ly);
-        unsigned pi = 0;
-        int kz = 0;
-        if (fold.P) {
-            pi = (unsigned)(fold.xmask >= 0 ? (i & fold.xmask) : i % fold.Lx);
-            kz = fold.kphase + k0;
-            if (kz >= fold.Lz) kz %= fold.Lz;
-        }
         const bool full = k0 + BZ <= nk;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = j0 + warp + c * NW;
             if (j >= ny) continue;
-            if (fold.P) {
-                const unsigned pj = pi + (unsigned)(fold.ymask >= 0 ? (j & fold.ymask) : j % fold.Ly) * (unsigned)fold.Lx;
-                if (kz + BZ <= fold.Lz) {                    // no wrap inside the brick (always true when BZ | Lz)
-                    const float *pp = fold.P + (pj + (unsigned)kz * pplane);
-#pragma unroll
-                    for (int k = 0; k < BZ; ++k) acc[c][k] += __ldg(pp + (size_t)k * pplane);
-                } else {
-                    int kk = kz;
-#pragma unroll
-                    for (int k = 0; k < BZ; ++k) {
-                        acc[c][k] += __ldg(fold.P + (pj + (unsigned)kk * pplane));
-                        if (++kk == fold.Lz) kk = 0;
-                    }
-                }
-            }
             float *o = out + ((size_t)i + (size_t)nx * j + plane * k0);
             if (full) {
 #pragma unroll
@@ -417,14 +423,19 @@ __device__ __forceinline__ float4 q4_ycontract(const float4 *uu, const float4 ty
     return nv;
 }
 
-// a += sum_f wz[f] * v[f], in the order every multiband kernel of this file uses
-__device__ __forceinline__ float4 q4_zcontract(float4 a, const float4 tz, const float4 (&v)[3])
+// band value of a lane's four samples (see band_value) and the canonical running sum
+__device__ __forceinline__ float4 q4_band_value(const float4 tz, const float4 (&v)[3])
 {
-    a.x = fmaf(tz.x, v[0].x, fmaf(tz.y, v[1].x, fmaf(tz.z, v[2].x, a.x)));
-    a.y = fmaf(tz.x, v[0].y, fmaf(tz.y, v[1].y, fmaf(tz.z, v[2].y, a.y)));
-    a.z = fmaf(tz.x, v[0].z, fmaf(tz.y, v[1].z, fmaf(tz.z, v[2].z, a.z)));
-    a.w = fmaf(tz.x, v[0].w, fmaf(tz.y, v[1].w, fmaf(tz.z, v[2].w, a.w)));
+    float4 a;
+    a.x = band_value(tz, v[0].x, v[1].x, v[2].x);
+    a.y = band_value(tz, v[0].y, v[1].y, v[2].y);
+    a.z = band_value(tz, v[0].z, v[1].z, v[2].z);
+    a.w = band_value(tz, v[0].w, v[1].w, v[2].w);
     return a;
+}
+__device__ __forceinline__ float4 q4_band_add(const float4 bv, const float4 s)
+{
+    return make_float4(__fadd_rn(bv.x, s.x), __fadd_rn(bv.y, s.y), __fadd_rn(bv.z, s.z), __fadd_rn(bv.w, s.w));
 }
 
 // ---- k_mb3d_brick4: same algorithm, four x-samples per thread --------------------------------------------------
@@ -451,7 +462,7 @@ k_mb3d_brick4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, i
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY, k0 = blockIdx.z * BZ;
-    if (tabs.wait_first) { chain_wait(); chain_release(); }
+    if (tabs.wait_first || fold.P) { chain_wait(); chain_release(); }   // tables / period block of the previous kernel
 
     q4_load_tables<BY, BZ, NT>(s_tab, tabs, i0, j0, k0, nx, ny, nk);
     __shared__ Q4Foot ft;
@@ -462,14 +473,36 @@ k_mb3d_brick4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, i
         q4_xpass<NT, POW2>(N, n, s_tab + b * PER_BAND, U4, s_rowoff, ft.row0[b], ft.row0[b + 1]);
     __syncthreads();
 
-    // ---- YZ pass for every band
+    // ---- running sums start from the period-block value (canonical summation: folded bands first).  Host guarantees
+    // nx % 4 == 0 and, when folding, Lx % 4 == 0: float4 loads and stores.
+    const int i = i0 + 4 * lane;
     float4 acc[C][BZ];
 #pragma unroll
     for (int c = 0; c < C; ++c)
 #pragma unroll
         for (int k = 0; k < BZ; ++k) acc[c][k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (fold.P) {
+        const unsigned pplane = (unsigned)(fold.Lx * fold.Ly);
+        const int ic = min(i, nx - 4);
+        const unsigned pi = (unsigned)(fold.xmask >= 0 ? (ic & fold.xmask) : ic % fold.Lx);
+        int kz = fold.kphase + k0;
+        if (kz >= fold.Lz) kz %= fold.Lz;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = min(j0 + warp + c * NW, ny - 1);
+            const unsigned pj = pi + (unsigned)(fold.ymask >= 0 ? (j & fold.ymask) : j % fold.Ly) * (unsigned)fold.Lx;
+            int kk = kz;
+#pragma unroll
+            for (int k = 0; k < BZ; ++k) {
+                acc[c][k] = __ldg(reinterpret_cast<const float4 *>(fold.P + (pj + (unsigned)kk * pplane)));
+                if (++kk == fold.Lz) kk = 0;
+            }
+        }
+    }
 
-    for (int b = 0; b < nbands; ++b) {
+
+    // ---- YZ pass for every band, highest scale first
+    for (int b = nbands - 1; b >= 0; --b) {
         const float4 *tY = s_tab + b * PER_BAND + BX, *tZ = tY + BY;
         const int my0 = __float_as_int(tY[0].w), mz0 = __float_as_int(tZ[0].w);
         const int slab4 = ft.ey[b] * 32;                         // one cz plane of this band's U in float4 units
@@ -496,40 +529,19 @@ k_mb3d_brick4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, i
                 }
             }
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                acc[c][k] = q4_zcontract(acc[c][k], tz, v[c]);
-            }
+            for (int c = 0; c < C; ++c) acc[c][k] = q4_band_add(q4_band_value(tz, v[c]), acc[c][k]);
         }
     }
 
-    // ---- epilogue (host guarantees nx % 4 == 0 and, when folding, Lx % 4 == 0): float4 loads and stores
-    if (!tabs.wait_first) { chain_wait(); chain_release(); }   // the period block is the previous kernel's output
-    const int i = i0 + 4 * lane;
+    // ---- epilogue: float4 streaming stores
+    if (!(tabs.wait_first || fold.P)) { chain_wait(); chain_release(); }   // nothing was read from the previous kernel so far
     if (i < nx) {
         const size_t plane = (size_t)nx * ny;
-        const unsigned pplane = (unsigned)(fold.Lx * fold.Ly);
-        unsigned pi = 0;
-        int kz = 0;
-        if (fold.P) {
-            pi = (unsigned)(fold.xmask >= 0 ? (i & fold.xmask) : i % fold.Lx);
-            kz = fold.kphase + k0;
-            if (kz >= fold.Lz) kz %= fold.Lz;
-        }
         const bool full = k0 + BZ <= nk;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = j0 + warp + c * NW;
             if (j >= ny) continue;
-            if (fold.P) {
-                const unsigned pj = pi + (unsigned)(fold.ymask >= 0 ? (j & fold.ymask) : j % fold.Ly) * (unsigned)fold.Lx;
-                int kk = kz;
-#pragma unroll
-                for (int k = 0; k < BZ; ++k) {
-                    const float4 pv = __ldg(reinterpret_cast<const float4 *>(fold.P + (pj + (unsigned)kk * pplane)));
-                    acc[c][k].x += pv.x; acc[c][k].y += pv.y; acc[c][k].z += pv.z; acc[c][k].w += pv.w;
-                    if (++kk == fold.Lz) kk = 0;
-                }
-            }
             float *o = out + ((size_t)i + (size_t)nx * j + plane * k0);
 #pragma unroll
             for (int k = 0; k < BZ; ++k) {
@@ -661,9 +673,8 @@ k_mb3d_col4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int
 
     const size_t plane = (size_t)nx * ny;
     float *o = out + ((size_t)i + (size_t)nx * j + plane * k0);
-    // one z step: the bands' contributions to sample plane k
-    auto zstep = [&](int k) {
-        float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    // one z step: the value of every band at sample plane k (each from zero, see band_value)
+    auto zstep = [&](int k, float4 (&bv)[NB]) {
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             const float4 tz = tZ[b][k];
@@ -675,14 +686,22 @@ k_mb3d_col4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int
                 unext[b] += slab4[b];
                 v[b][0] = v[b][1]; v[b][1] = v[b][2]; v[b][2] = nv;
             }
-            a = q4_zcontract(a, tz, v[b]);
+            bv[b] = q4_band_value(tz, v[b]);
         }
-        return a;
+    };
+    // canonical sum: period-block value (or 0) first, then the bands from the highest scale down
+    auto combine = [&](const float4 (&bv)[NB], const float4 pv) {
+        float4 s = pv;                                         // zero when nothing is folded
+#pragma unroll
+        for (int b = NB - 1; b >= 0; --b) s = q4_band_add(bv[b], s);
+        return s;
     };
     if constexpr (RING > 0) {
 #pragma unroll 4
         for (int k = 0; k < kmax; ++k) {
-            float4 a = zstep(k);
+            float4 bv[NB];
+            zstep(k, bv);
+            float4 pv = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             if (folded) {
                 if (k + RING - 1 < kmax) {                     // slot of plane k-1, consumed in the previous step
                     cp_async16(ring + ((k + RING - 1) % RING) * NT, pp);
@@ -690,10 +709,9 @@ k_mb3d_col4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int
                 }
                 cp_async_commit();
                 cp_async_wait<RING - 1>();                     // plane k has landed
-                const float4 pv = ring[(k % RING) * NT];
-                a.x += pv.x; a.y += pv.y; a.z += pv.z; a.w += pv.w;
+                pv = ring[(k % RING) * NT];
             }
-            __stcs(reinterpret_cast<float4 *>(o), a);
+            __stcs(reinterpret_cast<float4 *>(o), combine(bv, pv));
             o += plane;
         }
     } else {
@@ -702,16 +720,14 @@ k_mb3d_col4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int
             for (int d = 0; d < PF; ++d) {
                 const int k = kb + d;
                 if (k < kmax) {
-                    float4 a = zstep(k);
-                    if (folded) {
-                        const float4 pv = pq[d];
-                        if (k + PF < kmax) {
-                            pq[d] = __ldg(reinterpret_cast<const float4 *>(pp));
-                            if (++kk == fold.Lz) { kk = 0; pp = pcol; } else pp += pplane;
-                        }
-                        a.x += pv.x; a.y += pv.y; a.z += pv.z; a.w += pv.w;
+                    float4 bv[NB];
+                    zstep(k, bv);
+                    const float4 pv = pq[d];
+                    if (folded && k + PF < kmax) {
+                        pq[d] = __ldg(reinterpret_cast<const float4 *>(pp));
+                        if (++kk == fold.Lz) { kk = 0; pp = pcol; } else pp += pplane;
                     }
-                    __stcs(reinterpret_cast<float4 *>(o), a);
+                    __stcs(reinterpret_cast<float4 *>(o), combine(bv, pv));
                     o += plane;
                 }
             }
@@ -743,11 +759,11 @@ k_mb3d_gather(WnTileView t, WnTabs tabs, int nx, int ny, int nk, float *__restri
     if (i >= nx) return;
     const int n = t.n;
     float acc = 0.0f;
-    for (int b = 0; b < nbands; ++b) {
+    for (int b = nbands - 1; b >= 0; --b) {                    // canonical summation, highest scale first
         const int row = tabs_row(tabs, b);
         const float4 ax = __ldg(tabs.x + row * tabs.sx + i), ay = __ldg(tabs.y + row * tabs.sy + j),
                      az = __ldg(tabs.z + row * tabs.sz + tabs.kz0 + k);
-        const float wx[3] = { ax.x, ax.y, ax.z }, wy[3] = { ay.x, ay.y, ay.z }, wz[3] = { az.x, az.y, az.z };
+        const float wx[3] = { ax.x, ax.y, ax.z }, wy[3] = { ay.x, ay.y, ay.z };
         int cx[3], cy[3], cz[3];
 #pragma unroll
         for (int f = 0; f < 3; ++f) {
@@ -755,19 +771,18 @@ k_mb3d_gather(WnTileView t, WnTabs tabs, int nx, int ny, int nk, float *__restri
             cy[f] = tmodf(__float_as_int(ay.w) + f, n, t.pow2) * n;
             cz[f] = tmodf(__float_as_int(az.w) + f, n, t.pow2) * n * n;
         }
+        float vz[3];
 #pragma unroll
         for (int fz = 0; fz < 3; ++fz) {
-            float vy = 0.0f;
+            float ux[3];
 #pragma unroll
             for (int fy = 0; fy < 3; ++fy) {
                 const float *row = t.N + cy[fy] + cz[fz];
-                float vx = wx[0] * __ldg(row + cx[0]);
-                vx = fmaf(wx[1], __ldg(row + cx[1]), vx);
-                vx = fmaf(wx[2], __ldg(row + cx[2]), vx);
-                vy = fmaf(wy[fy], vx, vy);
+                ux[fy] = fmaf(wx[2], __ldg(row + cx[2]), fmaf(wx[1], __ldg(row + cx[1]), wx[0] * __ldg(row + cx[0])));
             }
-            acc = fmaf(wz[fz], vy, acc);
+            vz[fz] = fmaf(wy[2], ux[2], fmaf(wy[1], ux[1], wy[0] * ux[0]));     // same order as q4_ycontract
         }
+        acc = __fadd_rn(band_value(az, vz[0], vz[1], vz[2]), acc);
     }
     out[(size_t)i + (size_t)nx * ((size_t)j + (size_t)ny * k)] = acc;
 }
@@ -1111,6 +1126,18 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
         const int total_e = (int)(per_band * b.nbands);
         launch_chained(k_axis_tables, dim3(std::min((total_e + 255) / 256, 1184)), dim3(256), 0, st, c, b, 0, nz, tx, ty, tz);
         launched = 1;
+        // canonical order of the bands (see band_value): ascending scale, ties by index; table rows keep the caller's order
+        int order[WN_MAX_BANDS];
+        for (int i = 0; i < b.nbands; ++i) order[i] = i;
+        std::stable_sort(order, order + b.nbands, [&](int l, int r) { return b.scale[l] < b.scale[r]; });
+        WnBands sorted = b;
+        for (int i = 0; i < b.nbands; ++i) {
+            sorted.scale[i] = b.scale[order[i]];
+            sorted.weight[i] = b.weight[order[i]];
+            plan->direct_rows[i] = (unsigned char)order[i];
+        }
+        b = sorted;
+        plan->direct = b;
     }
     if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
     const HostAxes &hax = *static_cast<const HostAxes *>(plan->host_axes);
@@ -1132,15 +1159,17 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
                                    std::max(median_step(h_ys, ny, b.scale[i]), median_step(h_zs, nz, b.scale[i])));
         cost[i] = 1.0 + 1.2 * std::pow(st, 1.6);
     }
+    // candidates: the folded bands must be a suffix of the canonical order (their block holds the canonical sum of that
+    // suffix), so walk down from the highest scale and stop at the first band that does not repeat on this lattice
     if (budget > 0)
-        for (int i = 0; i < b.nbands; ++i) {
+        for (int i = b.nbands - 1; i >= 0; --i) {
             const int row = plan->direct_rows[i];
             Cand cd{i, axis_period(hax.ex(row), nx), axis_period(hax.ey(row), ny), axis_period(hax.ez(row), nz), 0};
             cd.vol = (long long)cd.px * cd.py * cd.pz;
-            if (cd.vol * 4 <= total) cand.push_back(cd);
+            if (cd.vol * 4 > total) break;
+            cand.push_back(cd);
         }
-    std::sort(cand.begin(), cand.end(), [](const Cand &a, const Cand &b2) { return a.vol < b2.vol; });
-    // grow the folded set in order of period volume; keep the prefix with the lowest estimated cost.  Period blocks
+    // grow the folded set one band at a time (highest scale first); keep the prefix with the lowest estimated cost.  Period blocks
     // nest (the block is evaluated by this same function), so band i of the prefix is charged on the block it
     // enlarges the fold to, plus the add of the previous level:
     //   cost = (sum_direct c_b + 0.3) * total + sum_{i folded} ((c_i + 0.3) * block_i + level)
@@ -1154,8 +1183,8 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
     int nfold = 0, ntrial = 0;
     for (const Cand &cd : cand) {
         const long long lx = lcm_capped(Lx, cd.px, nx), ly = lcm_capped(Ly, cd.py, ny), lz = lcm_capped(Lz, cd.pz, nz);
-        if (lx > nx || ly > ny || lz > nz) continue;
-        if (lx * ly * lz > budget || lx * ly * lz * 4 > total) continue;
+        if (lx > nx || ly > ny || lz > nz) break;
+        if (lx * ly * lz > budget || lx * ly * lz * 4 > total) break;
         Lx = lx; Ly = ly; Lz = lz;
         trial[cd.band] = true;
         ++ntrial;
