@@ -20,6 +20,7 @@ KNOBS = ("WN_COL4", "WN_FOLD_BUDGET", "WN_REPLICA_ORDER", "WN_BRICK", "WN_RING")
 VARIANTS = [
     ("default (col4, 512 MiB block, ring 8)", {}),
     ("ring 4", {"WN_RING": "4"}),
+    ("ring 8 also for the 512^3 block kernel", {"WN_RING": "8"}),
     ("register look-ahead 2", {"WN_RING": "-2"}),
     ("register look-ahead 4", {"WN_RING": "-4"}),
     ("plain block order", {"WN_REPLICA_ORDER": "0"}),
