@@ -76,6 +76,13 @@ const char *wn_version(void);
 uint64_t    wn_kernel_launches(const wn_ctx *ctx);
 /* CUDA-event time of the kernels enqueued by the most recent WN_HOST call on this context (ms) */
 float       wn_timing_last_ms(const wn_ctx *ctx);
+/* Host-only (no GPU needed): which bands a WN_EVAL_FAST wn_multiband3d_lattice call on these axes would evaluate once
+ * per period ("fold") at its top level for a tile of edge tile_n.  band_folded[nbands] receives 0/1 in the caller's
+ * band order, block[3] the period block Lx, Ly, Lz in samples (1,1,1 when nothing folds); *nfolded the count.  The
+ * decision never changes a result (canonical summation), only where the work is done. */
+int         wn_debug_fold_plan(const float *xs, int nx, const float *ys, int ny, const float *zs, int nz,
+                               const float *band_scale, int nbands, int tile_n,
+                               int *band_folded, int block[3], int *nfolded);
 
 /* ---- context ------------------------------------------------------------------------------ */
 int  wn_ctx_create(int device /* -1 = current */, wn_ctx **out);

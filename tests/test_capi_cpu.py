@@ -76,6 +76,53 @@ def test_fails_loudly_without_gpu():
     assert e.value.code == -2 and "no CPU fallback" in str(e.value)
 
 
+def test_fold_plan_host_logic(monkeypatch):
+    """The fold decision of the fast lattice path is pure host code (period detection on the axis tables + cost model):
+    config 3, its contiguous and block-cyclic shards, a non-commensurate lattice, a non-power-of-two tile."""
+    import numpy as np
+    wn = wnpkg.load()
+    sh = wnpkg.load_sub("sharding")
+    for k in ("WN_FOLD_BUDGET", "WN_FOLD_NEST"):
+        monkeypatch.delenv(k, raising=False)
+    ax = sh.lattice_axes_config3(1024)
+    scale, _, _ = sh.config3_bands(4, 8)
+    # whole volume: bands 5..8 repeat (periods 512/256/128/64 samples), band 4's period is the lattice itself
+    folded, block = wn.fold_plan(ax, ax, ax, scale, 128)
+    assert list(folded) == [False, True, True, True, True] and block == (512, 512, 512)
+    # the decision follows the bands, not their order in the call
+    perm = [3, 0, 4, 2, 1]
+    folded_p, block_p = wn.fold_plan(ax, ax, ax, scale[perm], 128)
+    assert list(folded_p) == [True, False, True, True, True] and block_p == block
+    # contiguous 128-slice slab (1/8 of the volume): no whole z period of band 5 -> the block spans the slab in z
+    folded, block = wn.fold_plan(ax, ax, ax[:128], scale, 128)
+    assert list(folded) == [False, True, True, True, True] and block == (512, 512, 128)
+    # block-cyclic shard of rank 3 of 8: slices congruent modulo 256 stay together -> z period 64 for band 5
+    zs = ax[sh.cyclic_slab_indices(1024, 3, 8)]
+    folded, block = wn.fold_plan(ax, ax, zs, scale, 128)
+    assert list(folded) == [False, True, True, True, True] and block == (512, 512, 64)
+    # a smaller budget (64 MiB = 2^24 samples) keeps band 5 per sample
+    monkeypatch.setenv("WN_FOLD_BUDGET", str(1 << 24))
+    folded, block = wn.fold_plan(ax, ax, ax, scale, 128)
+    assert list(folded) == [False, False, True, True, True] and block == (256, 256, 256)
+    monkeypatch.setenv("WN_FOLD_BUDGET", "0")
+    assert not wn.fold_plan(ax, ax, ax, scale, 128)[0].any()
+    monkeypatch.delenv("WN_FOLD_BUDGET")
+    # coordinates that are not commensurate with the tile never fold
+    irr = (np.arange(512, dtype=np.float32) * np.float32(0.0137)).astype(np.float32)
+    folded, block = wn.fold_plan(irr, irr, irr, scale, 128)
+    assert not folded.any() and block == (1, 1, 1)
+    # non-power-of-two tile (n=30), step 1/2 cell: periods 60 / 30 / 15 samples for scales 1 / 2 / 4.  A lattice this
+    # small is not worth a dependent launch per level (nothing folds) unless the per-level cost is set to zero; then the
+    # suffix of the canonical order that has whole periods on every axis folds: scale 1 has no whole z period in 64 slices
+    xs = np.arange(240, dtype=np.float32) * np.float32(0.5)
+    assert not wn.fold_plan(xs, xs[:120], xs[:64], [1.0, 2.0, 4.0, 0.25], 30)[0].any()
+    monkeypatch.setenv("WN_FOLD_LEVEL_COST", "0")
+    folded, block = wn.fold_plan(xs, xs[:120], xs[:64], [1.0, 2.0, 4.0, 0.25], 30)
+    assert list(folded) == [False, True, True, False] and block == (30, 30, 30)
+    folded, block = wn.fold_plan(xs, xs[:120], xs[:120], [1.0, 2.0, 4.0, 0.25], 30)
+    assert list(folded) == [True, True, True, False] and block == (60, 60, 60)
+
+
 def test_viewer_json_format_matches_reference_converter(golden_dir):
     """The JSON emitter reproduces threejs/convert_raw_to_json.py on the shipped .raw (reference present only)."""
     import json

@@ -309,9 +309,11 @@ def test_large_host_call_is_chunked_consistently(wn, gpu_tiles):
     assert_bits(host, dev.cpu().numpy(), "chunked host vs device")
 
 
-def test_folding_non_pow2_tile_and_periods(wn, oracle):
+def test_folding_non_pow2_tile_and_periods(wn, oracle, monkeypatch):
     """Periodic folding with a non-power-of-two tile (n=30) and non-power-of-two periods (60 / 30 / 15 samples):
-    exercises the `%` paths of the brick kernels, the float4 kernel with Lx % 4 == 0 and the scalar one otherwise."""
+    exercises the `%` paths of the brick kernels, the float4 kernel with Lx % 4 == 0 and the scalar one otherwise.
+    (Lattices this small only fold when the cost model's per-level launch cost is set to zero.)"""
+    monkeypatch.setenv("WN_FOLD_LEVEL_COST", "0")
     tile = oracle.generate_tile(30, 807, 3)
     w = wn.WaveletNoise(30, 807)
     w.generateNoiseTile3D()
@@ -389,12 +391,13 @@ def test_fast_result_does_not_depend_on_folding_or_kernel(wn, gpu_tiles, monkeyp
     assert_bits(got, base, "band order")
 
 
-def test_back_to_back_device_calls_with_tile_rebuilds(wn):
+def test_back_to_back_device_calls_with_tile_rebuilds(wn, monkeypatch):
     """Consecutive device-resident FAST calls without any synchronisation in between (the period-block chain of call
     i+1 runs on the side stream while call i's main kernel is still in flight), with different lattices and the tile
     rebuilt between some of them.  Every result must equal the exact kernel evaluated afterwards, call by call, on a
     second object that replays the same tile sequence."""
     import torch
+    monkeypatch.setenv("WN_FOLD_LEVEL_COST", "0")            # fold even on these small lattices: period-block scratch in flight
     ctx = wn.Context(0)
     ctx.use_torch_stream()
     w = wn.WaveletNoise(32, 77, ctx)

@@ -150,6 +150,20 @@ class Context:
 _DEFAULT = None
 
 
+def fold_plan(xs, ys, zs, band_scale, tile_n):
+    """Host-only diagnostic (no GPU): which bands a FAST multiband3D_lattice call on these axes folds at its top level.
+    Returns (folded flags per band in the given order, (Lx, Ly, Lz))."""
+    xs, ys, zs = _host(xs), _host(ys), _host(zs)
+    bs = _host(band_scale)
+    folded = np.zeros(max(bs.size, 1), np.int32)
+    block = np.zeros(3, np.int32)
+    n = C.c_int(0)
+    _lib.check(_lib.lib.wn_debug_fold_plan(xs.ctypes.data, xs.size, ys.ctypes.data, ys.size, zs.ctypes.data, zs.size,
+                                           bs.ctypes.data, bs.size, int(tile_n),
+                                           folded.ctypes.data_as(_lib.i32p), block.ctypes.data_as(_lib.i32p), C.byref(n)))
+    return folded[: bs.size].astype(bool), tuple(int(v) for v in block)
+
+
 def default_context():
     global _DEFAULT
     if _DEFAULT is None:

@@ -854,6 +854,21 @@ extern "C" int wn_multiband3d_lattice(const wn_tile *t, const float *xs, int nx,
     return r;
 }
 
+extern "C" int wn_debug_fold_plan(const float *xs, int nx, const float *ys, int ny, const float *zs, int nz,
+                                  const float *band_scale, int nbands, int tile_n, int *band_folded, int block[3],
+                                  int *nfolded)
+{
+    WN_REQUIRE(band_folded && block && nfolded, "wn_debug_fold_plan: NULL output");
+    WN_REQUIRE(tile_n >= 2, "wn_debug_fold_plan: tile_n must be >= 2 (got %d)", tile_n);
+    int r = check_axes(xs, nx, ys, ny, zs, nz, true);
+    if (r) return r;
+    WnBands b;
+    std::vector<float> ones((size_t)std::max(nbands, 1), 1.0f);
+    if ((r = make_bands(band_scale, ones.data(), nbands, 1.0f, &b))) return r;
+    *nfolded = wn_mb3d_fast_plan_host(xs, nx, ys, ny, zs, nz, b, tile_n, band_folded, block);
+    return WN_OK;
+}
+
 static int make_affine(ParamWriter &pw, const float origin[3], const float e1[3], const float *us, int nu,
                        const float e2[3], const float *vs, int nv, float pre, WnAffine *A)
 {

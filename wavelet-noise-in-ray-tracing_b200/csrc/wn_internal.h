@@ -95,6 +95,9 @@ int  wn_mb3d_fast_run(WnTileView t, WnLattice c, const float *h_ys, const float 
                       const unsigned char *all_rows, const WnFastPlan *plan, int k0, int nk, float *out, cudaStream_t st);
 void wn_mb3d_fast_finish(WnFastPlan *plan, cudaStream_t st);
 void wn_mb3d_fast_detach(WnFastPlan *plan, void **tab, void **P);
+// host-only fold decision of the top level (diagnostics / CPU tests); returns the number of folded bands
+int  wn_mb3d_fast_plan_host(const float *h_xs, int nx, const float *h_ys, int ny, const float *h_zs, int nz, WnBands b,
+                            int tile_n, int *folded, int block[3]);
 
 // 3D tile -> x-padded replica (row pitch n+WN_TILE_PAD, the extra cells wrap around)
 int wn_launch_pad_tile(const float *N, float *Npad, int n, cudaStream_t st);

@@ -1074,6 +1074,86 @@ long long lcm_capped(long long a, long long b, long long cap)
     return l > cap ? cap + 1 : l;
 }
 
+// ---- fold decision (pure host code; also behind wn_debug_fold_plan for the CPU tests) ------------------------------
+struct FoldDecision { int nfold; bool folded[WN_MAX_BANDS]; long long Lx, Ly, Lz; };
+
+// b: the bands of this (sub)lattice in canonical order, rows[i] = table row of band i; the lattice is the prefix
+// nx x ny x nz of the call's axes
+FoldDecision decide_fold(const HostAxes &hax, const unsigned char *rows, const WnBands &b, const float *h_xs,
+                         const float *h_ys, const float *h_zs, int nx, int ny, int nz)
+{
+    const long long total = (long long)nx * ny * nz;
+    long long budget = 1LL << 27;                              // samples in the period block: 512 MiB of scratch at most
+    if (const char *e = getenv("WN_FOLD_BUDGET")) budget = atoll(e);
+    struct Cand { int band; int px, py, pz; long long vol; };
+    std::vector<Cand> cand;
+    // relative per-sample cost of evaluating a band directly, from its step in tile cells per sample (fitted to the
+    // measured single-band times: 1 : 1.1 : 1.3 : 2 : 5.4 for steps 1/8 .. 2)
+    double cost[WN_MAX_BANDS];
+    auto median_step = [](const float *a, int len, float scale) {
+        if (len < 2) return 0.0;
+        const int m = len / 2;
+        return std::fabs(((double)a[m] - (double)a[m - 1]) * (double)scale);
+    };
+    for (int i = 0; i < b.nbands; ++i) {
+        const double st = std::max(median_step(h_xs, nx, b.scale[i]),
+                                   std::max(median_step(h_ys, ny, b.scale[i]), median_step(h_zs, nz, b.scale[i])));
+        cost[i] = 1.0 + 1.2 * std::pow(st, 1.6);
+    }
+    // candidates: the folded bands must be a suffix of the canonical order (their block holds the canonical sum of that
+    // suffix), so walk down from the highest scale and stop at the first band that does not repeat on this lattice
+    if (budget > 0)
+        for (int i = b.nbands - 1; i >= 0; --i) {
+            const int row = rows[i];
+            Cand cd{i, axis_period(hax.ex(row), nx), axis_period(hax.ey(row), ny), axis_period(hax.ez(row), nz), 0};
+            cd.vol = (long long)cd.px * cd.py * cd.pz;
+            if (cd.vol * 4 > total) break;
+            cand.push_back(cd);
+        }
+    // grow the folded set one band at a time (highest scale first); keep the prefix with the lowest estimated cost.  Period blocks
+    // nest (the block is evaluated by this same function), so band i of the prefix is charged on the block it
+    // enlarges the fold to, plus the add of the previous level:
+    //   cost = (sum_direct c_b + 0.3) * total + sum_{i folded} ((c_i + 0.3) * block_i + level)
+    // in units of one band-sample (~1 ps of GPU time); level = the latency of one more small dependent launch (~8 us).
+    double level_overhead = 8e6;
+    if (const char *e = getenv("WN_FOLD_LEVEL_COST")) level_overhead = atof(e);   // tests fold tiny lattices with 0
+    double direct_sum = 0.0;
+    for (int i = 0; i < b.nbands; ++i) direct_sum += cost[i];
+    double best = direct_sum * (double)total, nested_sum = 0.0;
+    long long Lx = 1, Ly = 1, Lz = 1, bLx = 1, bLy = 1, bLz = 1;
+    bool folded[WN_MAX_BANDS] = { false }, trial[WN_MAX_BANDS] = { false };
+    int nfold = 0, ntrial = 0;
+    for (const Cand &cd : cand) {
+        const long long lx = lcm_capped(Lx, cd.px, nx), ly = lcm_capped(Ly, cd.py, ny), lz = lcm_capped(Lz, cd.pz, nz);
+        if (lx > nx || ly > ny || lz > nz) break;
+        if (lx * ly * lz > budget || lx * ly * lz * 4 > total) break;
+        Lx = lx; Ly = ly; Lz = lz;
+        trial[cd.band] = true;
+        ++ntrial;
+        nested_sum += (cost[cd.band] + 0.3) * (double)(Lx * Ly * Lz) + level_overhead;
+        direct_sum -= cost[cd.band];
+        const double est = (direct_sum + 0.3) * (double)total + nested_sum;
+        if (est < best) {
+            best = est;
+            for (int i = 0; i < b.nbands; ++i) folded[i] = trial[i];
+            nfold = ntrial;
+            bLx = Lx; bLy = Ly; bLz = Lz;
+        }
+    }
+    FoldDecision fd;
+    fd.nfold = nfold;
+    for (int i = 0; i < WN_MAX_BANDS; ++i) fd.folded[i] = folded[i];
+    fd.Lx = bLx; fd.Ly = bLy; fd.Lz = bLz;
+    return fd;
+}
+
+// canonical order of the bands (see band_value): ascending scale, ties by index
+void canonical_order(const WnBands &b, int order[WN_MAX_BANDS])
+{
+    for (int i = 0; i < b.nbands; ++i) order[i] = i;
+    std::stable_sort(order, order + b.nbands, [&](int l, int r) { return b.scale[l] < b.scale[r]; });
+}
+
 } // namespace
 
 int wn_launch_pad_tile(const float *N, float *Npad, int n, cudaStream_t st)
@@ -1128,8 +1208,7 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
         launched = 1;
         // canonical order of the bands (see band_value): ascending scale, ties by index; table rows keep the caller's order
         int order[WN_MAX_BANDS];
-        for (int i = 0; i < b.nbands; ++i) order[i] = i;
-        std::stable_sort(order, order + b.nbands, [&](int l, int r) { return b.scale[l] < b.scale[r]; });
+        canonical_order(b, order);
         WnBands sorted = b;
         for (int i = 0; i < b.nbands; ++i) {
             sorted.scale[i] = b.scale[order[i]];
@@ -1141,64 +1220,10 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
     }
     if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
     const HostAxes &hax = *static_cast<const HostAxes *>(plan->host_axes);
-    const long long total = (long long)nx * ny * nz;
-    long long budget = 1LL << 27;                              // samples in the period block: 512 MiB of scratch at most
-    if (const char *e = getenv("WN_FOLD_BUDGET")) budget = atoll(e);
-    struct Cand { int band; int px, py, pz; long long vol; };
-    std::vector<Cand> cand;
-    // relative per-sample cost of evaluating a band directly, from its step in tile cells per sample (fitted to the
-    // measured single-band times: 1 : 1.1 : 1.3 : 2 : 5.4 for steps 1/8 .. 2)
-    double cost[WN_MAX_BANDS];
-    auto median_step = [](const float *a, int len, float scale) {
-        if (len < 2) return 0.0;
-        const int m = len / 2;
-        return std::fabs(((double)a[m] - (double)a[m - 1]) * (double)scale);
-    };
-    for (int i = 0; i < b.nbands; ++i) {
-        const double st = std::max(median_step(h_xs, nx, b.scale[i]),
-                                   std::max(median_step(h_ys, ny, b.scale[i]), median_step(h_zs, nz, b.scale[i])));
-        cost[i] = 1.0 + 1.2 * std::pow(st, 1.6);
-    }
-    // candidates: the folded bands must be a suffix of the canonical order (their block holds the canonical sum of that
-    // suffix), so walk down from the highest scale and stop at the first band that does not repeat on this lattice
-    if (budget > 0)
-        for (int i = b.nbands - 1; i >= 0; --i) {
-            const int row = plan->direct_rows[i];
-            Cand cd{i, axis_period(hax.ex(row), nx), axis_period(hax.ey(row), ny), axis_period(hax.ez(row), nz), 0};
-            cd.vol = (long long)cd.px * cd.py * cd.pz;
-            if (cd.vol * 4 > total) break;
-            cand.push_back(cd);
-        }
-    // grow the folded set one band at a time (highest scale first); keep the prefix with the lowest estimated cost.  Period blocks
-    // nest (the block is evaluated by this same function), so band i of the prefix is charged on the block it
-    // enlarges the fold to, plus the add of the previous level:
-    //   cost = (sum_direct c_b + 0.3) * total + sum_{i folded} ((c_i + 0.3) * block_i + level)
-    // in units of one band-sample (~1 ps of GPU time); level = the latency of one more small dependent launch (~8 us).
-    const double level_overhead = 8e6;
-    double direct_sum = 0.0;
-    for (int i = 0; i < b.nbands; ++i) direct_sum += cost[i];
-    double best = direct_sum * (double)total, nested_sum = 0.0;
-    long long Lx = 1, Ly = 1, Lz = 1, bLx = 1, bLy = 1, bLz = 1;
-    bool folded[WN_MAX_BANDS] = { false }, trial[WN_MAX_BANDS] = { false };
-    int nfold = 0, ntrial = 0;
-    for (const Cand &cd : cand) {
-        const long long lx = lcm_capped(Lx, cd.px, nx), ly = lcm_capped(Ly, cd.py, ny), lz = lcm_capped(Lz, cd.pz, nz);
-        if (lx > nx || ly > ny || lz > nz) break;
-        if (lx * ly * lz > budget || lx * ly * lz * 4 > total) break;
-        Lx = lx; Ly = ly; Lz = lz;
-        trial[cd.band] = true;
-        ++ntrial;
-        nested_sum += (cost[cd.band] + 0.3) * (double)(Lx * Ly * Lz) + level_overhead;
-        direct_sum -= cost[cd.band];
-        const double est = (direct_sum + 0.3) * (double)total + nested_sum;
-        if (est < best) {
-            best = est;
-            for (int i = 0; i < b.nbands; ++i) folded[i] = trial[i];
-            nfold = ntrial;
-            bLx = Lx; bLy = Ly; bLz = Lz;
-        }
-    }
-    Lx = bLx; Ly = bLy; Lz = bLz;
+    const FoldDecision fd = decide_fold(hax, plan->direct_rows, b, h_xs, h_ys, h_zs, nx, ny, nz);
+    const bool *folded = fd.folded;
+    const int nfold = fd.nfold;
+    const long long Lx = fd.Lx, Ly = fd.Ly, Lz = fd.Lz;
     if (nfold == 0) return launched;
     WnBands bf = b, bd = b;
     bf.nbands = bd.nbands = 0;
@@ -1246,6 +1271,33 @@ void wn_mb3d_fast_detach(WnFastPlan *plan, void **tab, void **P)
     plan->tab = nullptr;
     plan->host_axes = nullptr;
     plan->owns_tab = 0;
+}
+
+// Host-only: the top-level fold decision of a FAST lattice call (no device needed).  folded[i] refers to the caller's
+// band order; block = period block Lx, Ly, Lz (1, 1, 1 when nothing folds).
+int wn_mb3d_fast_plan_host(const float *h_xs, int nx, const float *h_ys, int ny, const float *h_zs, int nz, WnBands b,
+                           int tile_n, int *folded, int block[3])
+{
+    block[0] = block[1] = block[2] = 1;
+    for (int i = 0; i < b.nbands; ++i) folded[i] = 0;
+    if (nx <= 0 || ny <= 0 || nz <= 0 || b.nbands <= 0 || tile_n < 2) return 0;
+    HostAxes *hax = make_host_axes(h_xs, nx, h_ys, ny, h_zs, nz, b, tile_n);
+    int order[WN_MAX_BANDS];
+    canonical_order(b, order);
+    WnBands sorted = b;
+    unsigned char rows[WN_MAX_BANDS] = { 0 };
+    for (int i = 0; i < b.nbands; ++i) {
+        sorted.scale[i] = b.scale[order[i]];
+        sorted.weight[i] = b.weight[order[i]];
+        rows[i] = (unsigned char)order[i];
+    }
+    const FoldDecision fd = decide_fold(*hax, rows, sorted, h_xs, h_ys, h_zs, nx, ny, nz);
+    delete hax;
+    if (fd.nfold > 0) {
+        for (int i = 0; i < b.nbands; ++i) folded[order[i]] = fd.folded[i] ? 1 : 0;
+        block[0] = (int)fd.Lx; block[1] = (int)fd.Ly; block[2] = (int)fd.Lz;
+    }
+    return fd.nfold;
 }
 
 void wn_mb3d_fast_finish(WnFastPlan *plan, cudaStream_t st)
