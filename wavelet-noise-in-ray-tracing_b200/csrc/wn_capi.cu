@@ -810,6 +810,12 @@ extern "C" int wn_multiband3d_lattice(const wn_tile *t, const float *xs, int nx,
         });
     }
     WnFastPlan plan;
+    // Programmatic dependent launch helps when everything is on one stream (N=8-sized shard: 176 -> 157 us) and hurts
+    // with the side-stream chain (157 vs 145 us): early-launched CTAs of the next main kernel then sit on SM slots the
+    // high-priority chain needs during the tail of the current one.
+    static const int pdl_side_chain = [] { const char *e = getenv("WN_PDL_SIDE_CHAIN"); return e ? atoi(e) : 0; }();
+    static const int pdl_side_main = [] { const char *e = getenv("WN_PDL_SIDE_MAIN"); return e ? atoi(e) : 0; }();
+    plan.pdl = use_side ? pdl_side_chain : 1;
     cudaStream_t chain = use_side ? c->side : c->stream;
     const int gen = (int)(c->side_calls & 1);
     if (use_side) {
@@ -831,6 +837,7 @@ extern "C" int wn_multiband3d_lattice(const wn_tile *t, const float *xs, int nx,
     if (use_side) {
         WN_CUDA(cudaEventRecord(c->ev_side, c->side));
         WN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_side, 0));
+        plan.pdl = pdl_side_main;
     }
     if (space == WN_DEVICE)
         r = run_device(c, [&](cudaStream_t st) { return wn_mb3d_fast_run(tv, L, ys, zs, b, nullptr, &plan, 0, nz, out, st); });

@@ -87,6 +87,7 @@ struct WnFastPlan {
     float4 *tab;                // axis tables of the whole call: [x | y | z] x tab_bands rows (see WnTabs)
     int tab_bands, sx, sy, sz;
     int owns_tab;               // the top-level plan frees the tables
+    int pdl;                    // launch this plan's kernels with programmatic dependent launch (set before prepare / run)
     void *host_axes;            // host copy of the tables (period detection, brick planning), shared by nested plans
 };
 int  wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const float *h_ys, const float *h_zs, WnBands b,

@@ -58,6 +58,7 @@ struct WnTabs {
     int nb;                     // bands of this launch
     unsigned long long rowbits;  // table row of band b in bits [4b, 4b+4): no indexed kernel parameter, no local copy
     int wait_first;             // first kernel after k_axis_tables: must wait for its predecessor before reading the tables
+    int pdl;                    // host side only: launch with the programmatic stream serialisation attribute
 };
 static_assert(WN_MAX_BANDS <= 16, "rows are packed four bits each");
 __host__ __device__ __forceinline__ int tabs_row(const WnTabs &t, int b) { return (int)((t.rowbits >> (4 * b)) & 15ull); }
@@ -901,9 +902,11 @@ bool allow_smem(K kern, size_t smem)
 
 // launch with the programmatic stream serialisation attribute (WN_PDL=0: plain stream order, for A/B runs)
 template <typename... KArgs, typename... Args>
-cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+cudaError_t launch_chained(bool want_pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                           Args... args)
 {
-    static const bool pdl = [] { const char *e = getenv("WN_PDL"); return !e || atoi(e) != 0; }();
+    static const bool pdl_env = [] { const char *e = getenv("WN_PDL"); return !e || atoi(e) != 0; }();
+    const bool pdl = want_pdl && pdl_env;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -922,7 +925,7 @@ int launch_brick(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
     const size_t smem = plan.smem;
     if (!allow_smem(kern, smem)) return -1;
     dim3 grid((nx + 31) / 32, (ny + BY - 1) / BY, (nk + BZ - 1) / BZ);
-    launch_chained(kern, grid, dim3(NT), smem, st, t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, out);
+    launch_chained(tabs.pdl != 0, kern, grid, dim3(NT), smem, st, t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, out);
     return 1;
 }
 
@@ -934,7 +937,7 @@ int launch_brick4(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
     const size_t smem = plan.smem;
     if (!allow_smem(kern, smem)) return -1;
     dim3 grid((nx + 127) / 128, (ny + BY - 1) / BY, (nk + BZ - 1) / BZ);
-    launch_chained(kern, grid, dim3(NT), smem, st, t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, out);
+    launch_chained(tabs.pdl != 0, kern, grid, dim3(NT), smem, st, t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, out);
     return 1;
 }
 
@@ -959,7 +962,7 @@ int launch_col4(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
         }
     }
     dim3 grid((nx + 127) / 128, nyb * ord.zrep, ord.zper);
-    launch_chained(kern, grid, dim3(NT), smem, st, t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, ord, out);
+    launch_chained(tabs.pdl != 0, kern, grid, dim3(NT), smem, st, t.Npad, t.n, tabs, nx, ny, nk, plan.max_rows, fold, ord, out);
     return 1;
 }
 
@@ -1174,6 +1177,7 @@ WnTabs plan_tabs(const WnFastPlan *plan, const unsigned char *rows, int nb, int 
     tb.sx = plan->sx; tb.sy = plan->sy; tb.sz = plan->sz;
     tb.kz0 = kz0; tb.nb = nb;
     tb.wait_first = 1;
+    tb.pdl = plan->pdl;
     tb.rowbits = 0;
     for (int i = 0; i < nb; ++i) tb.rowbits |= (unsigned long long)(rows[i] & 15) << (4 * i);
     return tb;
@@ -1204,7 +1208,7 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
         if (cudaMallocAsync(&plan->tab, per_band * b.nbands * sizeof(float4), st) != cudaSuccess) return -1;
         float4 *tx = plan->tab, *ty = tx + (size_t)b.nbands * nx, *tz = ty + (size_t)b.nbands * ny;
         const int total_e = (int)(per_band * b.nbands);
-        launch_chained(k_axis_tables, dim3(std::min((total_e + 255) / 256, 1184)), dim3(256), 0, st, c, b, 0, nz, tx, ty, tz);
+        launch_chained(plan->pdl != 0, k_axis_tables, dim3(std::min((total_e + 255) / 256, 1184)), dim3(256), 0, st, c, b, 0, nz, tx, ty, tz);
         launched = 1;
         // canonical order of the bands (see band_value): ascending scale, ties by index; table rows keep the caller's order
         int order[WN_MAX_BANDS];
@@ -1331,6 +1335,6 @@ int wn_mb3d_fast_run(WnTileView t, WnLattice c, const float *h_ys, const float *
     for (int i = 0; i < WN_MAX_BANDS; ++i) ident[i] = (unsigned char)i;
     const WnTabs all = plan_tabs(plan, all_rows ? all_rows : ident, all_bands.nbands, k0);
     dim3 grid((nx + 255) / 256, ny, nk);
-    launch_chained(k_mb3d_gather, grid, dim3(256), 0, st, t, all, nx, ny, nk, out);
+    launch_chained(all.pdl != 0, k_mb3d_gather, grid, dim3(256), 0, st, t, all, nx, ny, nk, out);
     return 1;
 }
