@@ -228,12 +228,22 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+    # the clock sampler starts BEFORE the warm-up and rank 0 keeps stepping until its first sample has arrived: the
+    # start-up of nvidia-smi (NVML initialisation, first query) can hold up kernel launches for a millisecond or two,
+    # which is a fifth of the timed region at N=8 (50 steps x 0.15 ms); afterwards it only samples every 100 ms
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler_extra_steps = 0
+    if rank == 0 and sampler.proc:
+        t_wait = time.perf_counter()
+        while not sampler.lines and time.perf_counter() - t_wait < 3.0:
+            step()
+            torch.cuda.synchronize()
+            sampler_extra_steps += 1
+    barrier()
     launches0 = ctx.kernel_launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
@@ -246,6 +256,8 @@ def run_ours(args, rank, world, local_rank):
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     launches = ctx.kernel_launches - launches0
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["extra_warmup_steps_while_sampler_started"] = sampler_extra_steps
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
