@@ -49,15 +49,17 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, n_gpus=1):
         self.gpu = gpu_index
+        self.n_gpus = n_gpus            # > 1: sample GPUs 0..n_gpus-1 (one nvidia-smi process on rank 0 watches every rank's GPU)
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
+            which = str(self.gpu) if self.n_gpus <= 1 else ",".join(str(i) for i in range(self.n_gpus))
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)],
+                                          "-lms", "100", "-i", which],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -78,6 +80,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
+        per_gpu = {}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -85,13 +88,17 @@ class ClockSampler:
                 continue
             try:
                 sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                per_gpu.setdefault(f[0], []).append(float(f[1]))
             except ValueError:
                 continue
             for name, val in zip(names, f[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if len(per_gpu) > 1:
+            out["per_gpu_sm_mhz"] = {k: float(np.median(v)) for k, v in sorted(per_gpu.items())}
+        return out
 
 
 def profiled_traffic_bytes():
@@ -231,7 +238,7 @@ def run_ours(args, rank, world, local_rank):
     # the clock sampler starts BEFORE the warm-up and rank 0 keeps stepping until its first sample has arrived: the
     # start-up of nvidia-smi (NVML initialisation, first query) can hold up kernel launches for a millisecond or two,
     # which is a fifth of the timed region at N=8 (50 steps x 0.15 ms); afterwards it only samples every 100 ms
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, world)
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
@@ -259,7 +266,11 @@ def run_ours(args, rank, world, local_rank):
     if clocks is not None:
         clocks["extra_warmup_steps_while_sampler_started"] = sampler_extra_steps
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    per_rank_ms = [elapsed_ms / args.steps]
     if world > 1:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank_ms = [float(x.item()) / args.steps for x in every]       # which rank, if any, is the straggler
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     total_samples = VOLUME ** 3 * args.steps
@@ -344,7 +355,8 @@ def run_ours(args, rank, world, local_rank):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": elapsed_ms / args.steps, "per_rank_ms_per_step": per_rank_ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "WMultibandNoise 1024^3 bands 4-8 weighted 2^-(b-4), tile n=128 seed 12345 "
                                "(BASELINE config 3), z block-cyclic sharded (32-slice chunks)",
