@@ -841,9 +841,33 @@ inline void host_entry(float coord, float scale, int n, HostEntry &e, int &first
     e.cell = m < 0 ? m + n : m;
 }
 
+// number of leading coordinates of a[0..na) that are bitwise equal to b[0..nb)
+inline int same_prefix(const float *a, int na, const float *b, int nb)
+{
+    const int m = std::min(na, nb);
+    if (m > 0 && std::memcmp(a, b, (size_t)m * sizeof(float)) == 0) return m;
+    return 0;
+}
+
+// The tables are a few hundred KB: a fresh allocation per call would be an mmap / page-fault / munmap round trip
+// (about a third of the host cost of a call), so each host thread keeps one spare instance with its storage.
+thread_local HostAxes *t_spare_axes = nullptr;
+HostAxes *acquire_host_axes()
+{
+    HostAxes *h = t_spare_axes;
+    t_spare_axes = nullptr;
+    return h ? h : new HostAxes;
+}
+void release_host_axes(HostAxes *h)
+{
+    if (!h) return;
+    if (!t_spare_axes) t_spare_axes = h; else delete h;
+}
+
 HostAxes *make_host_axes(const float *xs, int nx, const float *ys, int ny, const float *zs, int nz, const WnBands &b, int n)
 {
-    HostAxes *h = new HostAxes;
+    HostAxes *h = acquire_host_axes();
+    h->runs = 0;
     h->nb = b.nbands; h->nx = nx; h->ny = ny; h->nz = nz;
     h->e.resize(h->per_band() * b.nbands);
     h->first.resize(h->per_band() * b.nbands);
@@ -852,8 +876,15 @@ HostAxes *make_host_axes(const float *xs, int nx, const float *ys, int ny, const
         int *f = h->first.data() + band * h->per_band();
         const float s = b.scale[band];
         for (int i = 0; i < nx; ++i) host_entry(xs[i], s, n, e[i], f[i]);
-        for (int i = 0; i < ny; ++i) host_entry(ys[i], s, n, e[nx + i], f[nx + i]);
-        for (int i = 0; i < nz; ++i) host_entry(zs[i], s, n, e[nx + ny + i], f[nx + ny + i]);
+        // volumes usually reuse one coordinate array for several axes: copy instead of recomputing (the entries of a
+        // coordinate do not depend on the axis it is used for)
+        const int ny_same = same_prefix(ys, ny, xs, nx), nz_same_x = same_prefix(zs, nz, xs, nx);
+        std::copy(e, e + ny_same, e + nx);
+        std::copy(f, f + ny_same, f + nx);
+        for (int i = ny_same; i < ny; ++i) host_entry(ys[i], s, n, e[nx + i], f[nx + i]);
+        std::copy(e, e + nz_same_x, e + nx + ny);
+        std::copy(f, f + nz_same_x, f + nx + ny);
+        for (int i = nz_same_x; i < nz; ++i) host_entry(zs[i], s, n, e[nx + ny + i], f[nx + ny + i]);
     }
     return h;
 }
@@ -1270,7 +1301,7 @@ void wn_mb3d_fast_detach(WnFastPlan *plan, void **tab, void **P)
 {
     *tab = plan->owns_tab ? plan->tab : nullptr;
     *P = plan->P;
-    if (plan->owns_tab) delete static_cast<HostAxes *>(plan->host_axes);
+    if (plan->owns_tab) release_host_axes(static_cast<HostAxes *>(plan->host_axes));
     plan->P = nullptr;
     plan->tab = nullptr;
     plan->host_axes = nullptr;
@@ -1296,7 +1327,7 @@ int wn_mb3d_fast_plan_host(const float *h_xs, int nx, const float *h_ys, int ny,
         rows[i] = (unsigned char)order[i];
     }
     const FoldDecision fd = decide_fold(*hax, rows, sorted, h_xs, h_ys, h_zs, nx, ny, nz);
-    delete hax;
+    release_host_axes(hax);
     if (fd.nfold > 0) {
         for (int i = 0; i < b.nbands; ++i) folded[order[i]] = fd.folded[i] ? 1 : 0;
         block[0] = (int)fd.Lx; block[1] = (int)fd.Ly; block[2] = (int)fd.Lz;
@@ -1309,7 +1340,7 @@ void wn_mb3d_fast_finish(WnFastPlan *plan, cudaStream_t st)
     if (plan->P) cudaFreeAsync(plan->P, st);
     plan->P = nullptr;
     if (plan->owns_tab && plan->tab) cudaFreeAsync(plan->tab, st);
-    if (plan->owns_tab) delete static_cast<HostAxes *>(plan->host_axes);
+    if (plan->owns_tab) release_host_axes(static_cast<HostAxes *>(plan->host_axes));
     plan->tab = nullptr;
     plan->host_axes = nullptr;
     plan->owns_tab = 0;
