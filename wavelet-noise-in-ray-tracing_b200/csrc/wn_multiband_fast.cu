@@ -443,7 +443,8 @@ __device__ __forceinline__ float4 q4_band_add(const float4 bv, const float4 s)
 // A CTA owns 128 x BY x BZ samples; lane l owns x = 4l..4l+3, so U rows, the y-contracted window, the accumulators,
 // the period-block loads and the output stores are all float4 (LDS.128 / LDG.128 / STG.128): the per-sample FMA
 // count is unchanged but every other instruction is amortised over four samples.  Used for small footprints
-// (bands with <= ~1 cell per sample); the per-sample arithmetic is identical to k_mb3d_brick.
+// (bands with <= ~1 cell per sample) when three or more bands are left per sample, and for the inner period blocks;
+// the per-sample arithmetic is identical to k_mb3d_brick.
 template <int BY, int BZ, int NT, bool POW2>
 __global__ void __launch_bounds__(NT, BY * BZ <= 64 ? 3 : 1)
 k_mb3d_brick4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int nk,
@@ -1087,8 +1088,9 @@ int brick_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsign
 // The tile is periodic (n cells), so whenever a band's sample lattice is commensurate with it -- coordinate i+P
 // lands on the same cell (mod n) with bit-identical weights as coordinate i -- that band's contribution repeats
 // with period P along the axis.  Such bands are evaluated once on their common period block (Lx x Ly x Lz samples,
-// by the same brick kernel) and added by index mod period in the main kernel's epilogue.  Detection is exact
-// (bitwise on the table entries the device will compute), so arbitrary coordinates simply do not fold.
+// by the same kernels) and their block value, read by index mod period, is the start of every sample's running sum
+// (canonical summation, see band_value).  Detection is exact (bitwise on the table entries the device will compute),
+// so arbitrary coordinates simply do not fold.
 // smallest P <= len/2 with entry[i+P] == entry[i] for all i; len when the axis is not periodic
 int axis_period(const HostEntry *e, int len)
 {
