@@ -155,3 +155,30 @@ def test_bench_helpers():
     s.proc = type("P", (), {"terminate": lambda self: None, "wait": lambda self, timeout=None: 0, "kill": lambda self: None})()
     out = s.stop()
     assert out["sm_mhz"] == 1957.5 and out["sm_max_mhz"] == 1965 and out["reasons"] == ["sw_power_cap"]
+
+
+def test_header_is_valid_c_and_links_from_c(tmp_path):
+    """include/wn_b200.h is a C header: a C99 translation unit that includes it compiles with -Wall -Werror -pedantic,
+    links against libwn_b200.so and can call the host-only entry points (what a C / cgo / JNI host would bind)."""
+    import subprocess
+    src = tmp_path / "host.c"
+    src.write_text('''
+#include "wn_b200.h"
+#include <stdio.h>
+int main(void) {
+    float ax[64]; int folded[2], block[3], n = -1, i;
+    const float scale[2] = { 8.0f, 64.0f };
+    for (i = 0; i < 64; ++i) ax[i] = (float)i / 64.0f * 4.0f;
+    if (wn_adjust_tile_size(31) != 32) return 1;
+    if (wn_debug_fold_plan(ax, 64, ax, 64, ax, 64, scale, 2, 32, folded, block, &n) != WN_OK) return 2;
+    if (wn_debug_fold_plan(ax, 64, ax, 64, ax, 64, scale, 2, 1, folded, block, &n) != WN_EINVAL) return 3;
+    printf("%s folded=%d\\n", wn_version(), n);
+    return 0;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = os.path.join(ROOT, "wavelet-noise-in-ray-tracing_b200")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-lwn_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "folded=" in out
