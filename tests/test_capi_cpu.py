@@ -182,3 +182,49 @@ int main(void) {
                     str(src), "-o", str(exe), "-L", libdir, "-lwn_b200", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert "folded=" in out
+
+
+def test_fold_plan_properties_on_random_lattices(monkeypatch):
+    """Randomised host-logic check of the fold planner: the folded bands are a suffix of the ascending-scale order, the
+    period block fits the lattice and shrinks it at least 4x, and every folded band really repeats with the block's
+    periods (axis-table entries recomputed here in numpy float32: same weights, same cell modulo the tile)."""
+    import numpy as np
+    wn = wnpkg.load()
+    monkeypatch.setenv("WN_FOLD_LEVEL_COST", "0")
+    rs = np.random.RandomState(11)
+
+    def entries(coords, scale, n):
+        a = coords.astype(np.float32) * np.float32(scale) - np.float32(0.5)
+        mid = np.ceil(a).astype(np.int64)
+        t = mid.astype(np.float32) - a
+        w0 = t * t * np.float32(0.5)
+        s1 = np.float32(1.0) - t
+        w2 = s1 * s1 * np.float32(0.5)
+        w1 = np.float32(1.0) - w0 - w2
+        return np.stack([w0.view(np.uint32), w1.view(np.uint32), w2.view(np.uint32), ((mid - 1) % n).astype(np.uint32)], -1)
+
+    folded_cases = 0
+    for _ in range(60):
+        n = int(rs.choice([8, 16, 30, 32, 62, 128]))
+        dims = [int(rs.choice([12, 37, 64, 96, 128, 200, 256])) for _ in range(3)]
+        step = float(rs.choice([0.125, 0.25, 0.5, 1.0, 0.3, 1.0 / 3.0]))
+        offs = [float(rs.choice([0.0, 0.5, 3.25, -7.0])) for _ in range(3)]
+        axes = [(np.arange(d, dtype=np.float32) * np.float32(step) + np.float32(o)).astype(np.float32) for d, o in zip(dims, offs)]
+        nb = int(rs.randint(1, 7))
+        scale = rs.choice([0.25, 0.5, 1.0, 2.0, 4.0, 8.0, 3.0], nb, replace=True).astype(np.float32)
+        folded, block = wn.fold_plan(axes[0], axes[1], axes[2], scale, n)
+        order = np.argsort(scale, kind="stable")
+        flags = folded[order]
+        assert not (flags[:-1] & ~flags[1:]).any(), (scale, folded)           # suffix of the canonical order
+        if not folded.any():
+            assert block == (1, 1, 1)
+            continue
+        folded_cases += 1
+        assert all(1 <= b <= d for b, d in zip(block, dims))
+        assert block[0] * block[1] * block[2] * 4 <= dims[0] * dims[1] * dims[2]
+        for b in np.flatnonzero(folded):
+            for ax, L in zip(axes, block):
+                e = entries(ax, scale[b], n)
+                if L < len(ax):
+                    assert (e[L:] == e[:-L]).all(), (n, step, scale[b], L)
+    assert folded_cases >= 10
