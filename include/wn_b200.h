@@ -194,6 +194,16 @@ int  wn_eval3d_grid(const wn_tile *tile, const float origin[3],
  * precision, un-fused, result narrowed to float on store (experient/main.cpp:104,122). */
 int  wn_perlin_create(wn_ctx *ctx, const int32_t perm512_host[512], wn_perlin **out);
 int  wn_perlin_destroy(wn_perlin *pn);
+/* Arithmetic of the float batch calls below (points / lattice / grid).  WN_PERLIN_F64 (default): the reference's
+ * double-precision, un-fused operation order -- bit-identical to PerlinNoise::noise narrowed to float.
+ * WN_PERLIN_F32: single precision with FMAs, within 1e-5 * 2 (the noise range) of the FP64 result for float-valued
+ * coordinates; opt-in fast mode (hard part 6).  Texture hooks always run FP64. */
+#define WN_PERLIN_F64    0
+#define WN_PERLIN_F32    1
+int  wn_perlin_set_precision(wn_perlin *pn, int precision);
+/* double coordinates in (xyz per point), double noise out: the scalar signature of PerlinNoise::noise(double x,
+ * double y, double z) (experient/PerlinNoise.hpp:36-56, perlin.h:42-62) without narrowing at either end. */
+int  wn_perlin_points_f64(const wn_perlin *pn, const double *p, size_t count, double *out, int space);
 int  wn_perlin_points(const wn_perlin *pn, const float *p, size_t count, float pre_scale,
                       float *out, int space);
 int  wn_perlin_lattice(const wn_perlin *pn, const float *xs, int nx, const float *ys, int ny,

@@ -20,6 +20,8 @@ always host-side.
 import ctypes as C
 import sys
 
+import weakref
+
 import numpy as np
 
 from . import _lib
@@ -106,9 +108,14 @@ class Context:
         dev, sms = C.c_int(), C.c_int()
         check(lib.wn_ctx_device(self.h, C.byref(dev), C.byref(sms)))
         self.device, self.sm_count = dev.value, sms.value
+        self._children = weakref.WeakSet()      # tiles / Perlin tables created on this context
 
     def close(self):
+        """Destroys the context.  Objects created on it release their device state first (a tile or Perlin handle
+        must not outlive its wn_ctx: wn_tile_destroy dereferences it)."""
         if getattr(self, "h", None):
+            for child in list(getattr(self, "_children", ())):
+                child._release()
             lib.wn_ctx_destroy(self.h)
             self.h = None
 
@@ -208,19 +215,24 @@ class WaveletNoise:
         self._dims = 0
         self._host = None
         self._fresh = True              # the host generator has not been used yet (the first fill may run on the GPU)
+        self.ctx._children.add(self)
 
     def __del__(self):
         try:
-            self._drop_tile()
+            self._release()
             if getattr(self, "_rng", None):
                 lib.wn_rng_destroy(self._rng)
                 self._rng = None
         except Exception:
             pass
 
+    def _release(self):
+        self._drop_tile()
+
     def _drop_tile(self):
         if getattr(self, "_tile", None):
-            lib.wn_tile_destroy(self._tile)
+            if getattr(self.ctx, "h", None):     # a closed context has already released this tile
+                lib.wn_tile_destroy(self._tile)
             self._tile = None
 
     def _new_tile(self, dims):
@@ -466,21 +478,39 @@ class PerlinNoise:
         h = C.c_void_p()
         check(lib.wn_perlin_create(self.ctx.h, C.c_void_p(self.p.ctypes.data), C.byref(h)))
         self.h = h
+        self.ctx._children.add(self)
 
     def __del__(self):
         try:
-            if getattr(self, "h", None):
-                lib.wn_perlin_destroy(self.h)
-                self.h = None
+            self._release()
         except Exception:
             pass
 
+    def _release(self):
+        if getattr(self, "h", None):
+            if getattr(self.ctx, "h", None):
+                lib.wn_perlin_destroy(self.h)
+            self.h = None
+
+    def set_precision(self, precision):
+        """WN_PERLIN_F64 (default, bit-identical to the reference) or WN_PERLIN_F32 (fast mode, <= 1e-5 * range) for
+        the float batch calls noise_points / noise_lattice / noise_grid."""
+        check(lib.wn_perlin_set_precision(self.h, int(precision)))
+
     def noise(self, x, y=None, z=0.0):
-        """noise(x,y,z) / noise(x,y) / noise(point3).  Coordinates are narrowed to float32 first: every caller
-        in the reference passes float-valued doubles (experient/main.cpp:104,122; texture.h:39-40)."""
+        """noise(x,y,z) / noise(x,y) / noise(point3): double coordinates in, double noise out, like the reference's
+        signature (experient/PerlinNoise.hpp:36) -- nothing is narrowed to float."""
         if y is None:
             x, y, z = x
-        return float(self.noise_points(np.array([[x, y, z]], np.float32))[0])
+        return float(self.noise_points_f64(np.array([[x, y, z]], np.float64))[0])
+
+    def noise_points_f64(self, pts):
+        """Host float64 points (n, 3) -> float64 noise (wn_perlin_points_f64)."""
+        pts = np.ascontiguousarray(pts, np.float64)
+        out = np.empty(pts.size // 3, np.float64)
+        check(lib.wn_perlin_points_f64(self.h, C.c_void_p(pts.ctypes.data), pts.size // 3, C.c_void_p(out.ctypes.data),
+                                       WN_HOST))
+        return out
 
     def noise_points(self, pts, pre_scale=1.0, out=None):
         ptr, space, keep = _in(pts)

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libwn_b200.so")
 WN_HOST, WN_DEVICE = 0, 1
 WN_TILE_DEFAULT, WN_TILE_ODD_OFFSET = 0, 1
 WN_EVAL_FAST, WN_EVAL_EXACT = 0, 1
+WN_PERLIN_F64, WN_PERLIN_F32 = 0, 1
 WN_ENODEVICE = -2
 
 f32p = C.POINTER(C.c_float)
@@ -72,6 +73,8 @@ SIGNATURES = {
     "wn_eval3d_grid": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.c_float, vp, C.c_int]),
     "wn_perlin_create": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "wn_perlin_destroy": (C.c_int, [vp]),
+    "wn_perlin_set_precision": (C.c_int, [vp, C.c_int]),
+    "wn_perlin_points_f64": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_int]),
     "wn_perlin_points": (C.c_int, [vp, vp, C.c_size_t, C.c_float, vp, C.c_int]),
     "wn_perlin_lattice": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int]),
     "wn_perlin_grid": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, vp, C.c_int]),

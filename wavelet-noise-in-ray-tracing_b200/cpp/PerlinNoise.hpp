@@ -2,9 +2,10 @@
 // (reference: experient/PerlinNoise.hpp:9-61; the renderer's `class perlin`, perlin.h:14-72, is the same algorithm).
 // The permutation table is built exactly like the reference's constructor (iota + std::shuffle with
 // std::mt19937(seed), duplicated to 512 entries); noise() runs the double-precision, un-fused kernel in
-// libwn_b200.so.  Scalar noise() calls are 1-point launches (correct but slow); drivers should use the
-// batch methods.  Coordinates are float-valued in every reference caller (experient/main.cpp:104,122;
-// texture.h:39-40), so the ABI takes float32 coordinates and promotes them to double on the device.
+// libwn_b200.so.  Scalar noise() calls are 1-point launches (correct but slow) through the double-in /
+// double-out entry wn_perlin_points_f64; drivers should use the batch methods.  Coordinates are float-valued in
+// every reference caller (experient/main.cpp:104,122; texture.h:39-40), so the BATCH entries take float32
+// coordinates and promote them to double on the device.
 #ifndef PERLINNOISE_HPP
 #define PERLINNOISE_HPP
 
@@ -38,11 +39,12 @@ class PerlinNoise {
     }
     PerlinNoise& operator=(const PerlinNoise&) = delete;
 
+    // double coordinates in, double noise out, like the reference (experient/PerlinNoise.hpp:36): nothing is narrowed
     double noise(double x, double y, double z) const
     {
-        const float q[3] = {(float)x, (float)y, (float)z};
-        float out = 0.0f;
-        wnb::check(wn_perlin_points(dev, q, 1, 1.0f, &out, WN_HOST));
+        const double q[3] = {x, y, z};
+        double out = 0.0;
+        wnb::check(wn_perlin_points_f64(dev, q, 1, &out, WN_HOST));
         return out;
     }
     double noise(double x, double y) const { return noise(x, y, 0.0); }

@@ -10,6 +10,7 @@
 #include "WaveletNoise.h"
 
 #include <cmath>
+#include <cstring>
 #include <mutex>
 #include <stdexcept>
 #include <unordered_map>
@@ -24,7 +25,25 @@ struct DeviceTile {
     int dims = 0;
     size_t count = 0;           // elements uploaded (to detect a stale entry after the vector changed)
     const float* host = nullptr;
+    unsigned long long print = 0;   // content fingerprint of the host coefficients the device tile was built from
 };
+
+// FNV-1a over up to 1024 evenly spaced coefficients (bit patterns).  `a = b` between two generated objects of the
+// same size reuses a's vector storage, so pointer and size alone cannot tell that the coefficients changed.
+unsigned long long fingerprint(const std::vector<float>& v)
+{
+    unsigned long long h = 1469598103934665603ull ^ v.size();
+    if (v.empty()) return h;
+    const size_t step = v.size() > 1024 ? v.size() / 1024 : 1;
+    for (size_t i = 0; i < v.size(); i += step) {
+        unsigned u;
+        std::memcpy(&u, &v[i], sizeof(u));
+        h = (h ^ u) * 1099511628211ull;
+    }
+    unsigned u;
+    std::memcpy(&u, &v.back(), sizeof(u));
+    return (h ^ u) * 1099511628211ull;
+}
 
 
 std::mutex g_mu;
@@ -69,15 +88,18 @@ wn_tile* tile_of(const WaveletNoise& noise)
     wn_ctx* ctx = context();
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_tiles.find(&noise);
-    if (it != g_tiles.end() && it->second.count == coeff.size() && it->second.host == coeff.data()) return it->second.tile;
-    // a copy of an object (implicit copy constructor) or a moved vector: upload the host coefficients
+    const unsigned long long print = fingerprint(coeff);
+    if (it != g_tiles.end() && it->second.count == coeff.size() && it->second.host == coeff.data() &&
+        it->second.print == print)
+        return it->second.tile;
+    // a copy of an object (implicit copy constructor / copy assignment) or a moved vector: upload the host coefficients
     drop_locked(&noise);
     const int dims = infer_dims(coeff.size(), noise.getTileSize());
     if (dims == 0) throw std::runtime_error("wn_b200: WaveletNoise holds no generated tile");
     DeviceTile dt;
     check(wn_tile_create(ctx, noise.getTileSize(), dims, WN_TILE_DEFAULT, &dt.tile));
     check(wn_tile_upload(dt.tile, coeff.data(), WN_HOST));
-    dt.dims = dims; dt.count = coeff.size(); dt.host = coeff.data();
+    dt.dims = dims; dt.count = coeff.size(); dt.host = coeff.data(); dt.print = print;
     g_tiles[&noise] = dt;
     return dt.tile;
 }
@@ -129,7 +151,7 @@ static void generate_on_gpu(const WaveletNoise* self, int n, int dims, unsigned 
     }
     coeff.resize(count);
     wnb::check(wn_tile_download(dt.tile, coeff.data(), WN_HOST));
-    dt.dims = dims; dt.count = count; dt.host = coeff.data();
+    dt.dims = dims; dt.count = count; dt.host = coeff.data(); dt.print = fingerprint(coeff);
     std::lock_guard<std::mutex> lk(g_mu);
     drop_locked(self);
     g_tiles[self] = dt;

@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <numeric>
 #include <random>
@@ -78,7 +79,7 @@ struct wn_ctx {
     uint64_t side_calls = 0;
     // double-buffered staging for WN_HOST calls
     WnBuf in[2], aux[2], outb[2];
-    cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
+    cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_k[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
     WnBuf params;                        // coordinate axes etc. for the call in flight
     std::vector<char> h_params;          // host staging of the same block
     WnBuf stats_partial;
@@ -109,6 +110,40 @@ static int buf_reserve(WnBuf &b, size_t bytes)
     return WN_OK;
 }
 
+// library-private scratch pool of a device (see wn_internal.h); created on first use, lives until process exit
+static cudaMemPool_t scratch_pool(int device)
+{
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        unsigned long long keep = ~0ull;             // recycle, do not return scratch to the OS between calls
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        pools[device] = pool;
+    }
+    return pools[device];
+}
+
+cudaError_t wn_scratch_alloc(void **p, size_t bytes, cudaStream_t st)
+{
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return e;
+    cudaMemPool_t pool = scratch_pool(device);
+    if (!pool) return cudaErrorMemoryAllocation;
+    return cudaMallocFromPoolAsync(p, bytes, pool, st);
+}
+
+static void ctx_release(wn_ctx *c);
+
 extern "C" int wn_ctx_create(int device, wn_ctx **out)
 {
     WN_REQUIRE(out, "wn_ctx_create: out is NULL");
@@ -132,33 +167,67 @@ extern "C" int wn_ctx_create(int device, wn_ctx **out)
     if (!c) return wn_fail(WN_ENOMEM, "out of host memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    WN_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    WN_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
-    WN_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+    // a failure below releases what was created so far (streams, events, the context itself)
+#define WN_CUDA_CTX(call)                                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx_release(c);                                                                        \
+            return wn_fail(WN_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                          \
+    } while (0)
+    WN_CUDA_CTX(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    WN_CUDA_CTX(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    WN_CUDA_CTX(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     {
         int least = 0, greatest = 0;
-        WN_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        WN_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, greatest));
-        WN_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
-        WN_CUDA(cudaEventCreateWithFlags(&c->ev_tile, cudaEventDisableTiming));
-        for (int i = 0; i < 2; ++i) WN_CUDA(cudaEventCreateWithFlags(&c->ev_main[i], cudaEventDisableTiming));
-    }
-    {   // stream-ordered scratch (filter temporaries, axis tables, period blocks) is recycled, not returned to the OS
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
+        WN_CUDA_CTX(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        WN_CUDA_CTX(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, greatest));
+        WN_CUDA_CTX(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+        WN_CUDA_CTX(cudaEventCreateWithFlags(&c->ev_tile, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) WN_CUDA_CTX(cudaEventCreateWithFlags(&c->ev_main[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < 2; ++i) {
-        WN_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
-        WN_CUDA(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
-        WN_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+        WN_CUDA_CTX(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        WN_CUDA_CTX(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+        WN_CUDA_CTX(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+    }
+#undef WN_CUDA_CTX
+    if (!scratch_pool(device)) {
+        ctx_release(c);
+        return wn_fail(WN_ECUDA, "could not create the library's scratch memory pool on device %d", device);
     }
     *out = c;
     return WN_OK;
+}
+
+// everything a context owns; members that were never created are null (partial construction)
+static void ctx_release(wn_ctx *c)
+{
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->in[i].p); cudaFree(c->aux[i].p); cudaFree(c->outb[i].p);
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (c->deferred[i].pending && c->side) { cudaFreeAsync(c->deferred[i].tab, c->side); cudaFreeAsync(c->deferred[i].P, c->side); }
+        if (c->ev_main[i]) cudaEventDestroy(c->ev_main[i]);
+    }
+    if (c->side) cudaStreamSynchronize(c->side);
+    cudaFree(c->params.p);
+    cudaFree(c->params_side.p);
+    cudaFree(c->stats_partial.p);
+    if (c->ev_side) cudaEventDestroy(c->ev_side);
+    if (c->ev_tile) cudaEventDestroy(c->ev_tile);
+    if (c->side) cudaStreamDestroy(c->side);
+    for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->h2d) cudaStreamDestroy(c->h2d);
+    if (c->d2h) cudaStreamDestroy(c->d2h);
+    cudaGetLastError();
+    delete c;
 }
 
 extern "C" int wn_ctx_destroy(wn_ctx *c)
@@ -166,23 +235,7 @@ extern "C" int wn_ctx_destroy(wn_ctx *c)
     if (!c) return WN_OK;
     DeviceGuard g(c->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 2; ++i) {
-        cudaFree(c->in[i].p); cudaFree(c->aux[i].p); cudaFree(c->outb[i].p);
-        cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_k[i]); cudaEventDestroy(c->ev_out[i]);
-    }
-    for (int i = 0; i < 2; ++i) {
-        if (c->deferred[i].pending) { cudaFreeAsync(c->deferred[i].tab, c->side); cudaFreeAsync(c->deferred[i].P, c->side); }
-        cudaEventDestroy(c->ev_main[i]);
-    }
-    cudaStreamSynchronize(c->side);
-    cudaFree(c->params.p);
-    cudaFree(c->params_side.p);
-    cudaFree(c->stats_partial.p);
-    cudaEventDestroy(c->ev_side); cudaEventDestroy(c->ev_tile);
-    cudaStreamDestroy(c->side);
-    for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
-    cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->h2d); cudaStreamDestroy(c->d2h);
-    delete c;
+    ctx_release(c);
     return WN_OK;
 }
 
@@ -512,8 +565,8 @@ static int tile_build_device(wn_tile *t, const float *dR)
     cudaStream_t st = c->stream;
     const size_t bytes = t->count * sizeof(float);
     float *t1 = nullptr, *t2 = nullptr;
-    WN_CUDA(cudaMallocAsync(&t1, bytes, st));
-    WN_CUDA(cudaMallocAsync(&t2, bytes, st));
+    WN_CUDA(wn_scratch_alloc((void **)&t1, bytes, st));
+    WN_CUDA(wn_scratch_alloc((void **)&t2, bytes, st));
     int nl = 0, r;
     const bool odd = (t->flags & WN_TILE_ODD_OFFSET) != 0;
     if (t->dims == 3) {
@@ -549,7 +602,7 @@ extern "C" int wn_tile_build_from_gaussian(wn_tile *t, const float *R, int space
     WN_REQUIRE(space == WN_HOST, "bad space %d", space);
     float *dR = nullptr;
     const size_t bytes = t->count * sizeof(float);
-    WN_CUDA(cudaMallocAsync(&dR, bytes, c->stream));
+    WN_CUDA(wn_scratch_alloc((void **)&dR, bytes, c->stream));
     WN_CUDA(cudaMemcpyAsync(dR, R, bytes, cudaMemcpyHostToDevice, c->stream));
     timing_begin(c);
     timing_mark(c, c->stream);
@@ -569,8 +622,8 @@ extern "C" int wn_tile_build_seeded(wn_tile *t, unsigned seed, unsigned long lon
     cudaStream_t st = c->stream;
     float *dR = nullptr;
     unsigned long long *dacc = nullptr;
-    WN_CUDA(cudaMallocAsync(&dR, t->count * sizeof(float), st));
-    WN_CUDA(cudaMallocAsync(&dacc, 2 * sizeof(unsigned long long), st));
+    WN_CUDA(wn_scratch_alloc((void **)&dR, t->count * sizeof(float), st));
+    WN_CUDA(wn_scratch_alloc((void **)&dacc, 2 * sizeof(unsigned long long), st));
     int rc = WN_OK;
     for (int margin = 20; ; margin *= 4) {                 // 2 % more attempts than expected; never short in practice
         timing_begin(c);
@@ -948,6 +1001,7 @@ extern "C" int wn_eval3d_grid(const wn_tile *t, const float origin[3], const flo
 struct wn_perlin {
     wn_ctx *ctx = nullptr;
     int32_t *d = nullptr;
+    int fast = 0;                        // WN_PERLIN_F32: FP32 kernel for the float batch calls
 };
 
 extern "C" int wn_perlin_create(wn_ctx *c, const int32_t perm[512], wn_perlin **out)
@@ -977,6 +1031,32 @@ extern "C" int wn_perlin_destroy(wn_perlin *p)
     return WN_OK;
 }
 
+extern "C" int wn_perlin_set_precision(wn_perlin *pn, int precision)
+{
+    WN_REQUIRE(pn, "wn_perlin_set_precision: perlin is NULL");
+    WN_REQUIRE(precision == WN_PERLIN_F64 || precision == WN_PERLIN_F32, "wn_perlin_set_precision: bad precision %d", precision);
+    pn->fast = precision == WN_PERLIN_F32;
+    return WN_OK;
+}
+
+// double coordinates in, double noise out: the scalar signature of PerlinNoise::noise (PerlinNoise.hpp:36, perlin.h:42)
+extern "C" int wn_perlin_points_f64(const wn_perlin *pn, const double *p, size_t count, double *out, int space)
+{
+    WN_REQUIRE(pn, "wn_perlin_points_f64: perlin is NULL");
+    WN_NEED_SPACE(space);
+    if (!count) return WN_OK;
+    WN_REQUIRE(p && out, "wn_perlin_points_f64: NULL buffer");
+    wn_ctx *c = pn->ctx;
+    DeviceGuard g(c->device);
+    const int32_t *perm = pn->d;
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_perlin_points_f64(perm, p, count, out, st); });
+    ChunkIO io; io.in = p; io.in_item = 3 * sizeof(double); io.out = out; io.out_item = sizeof(double);
+    return run_chunked_host(c, count, kChunkSamples / 2, io, [&](void *din, void *, float *dout, size_t, size_t cnt, cudaStream_t st) {
+        return wn_launch_perlin_points_f64(perm, (const double *)din, cnt, (double *)dout, st);
+    });
+}
+
 extern "C" int wn_perlin_points(const wn_perlin *pn, const float *p, size_t count, float pre, float *out, int space)
 {
     WN_REQUIRE(pn, "wn_perlin_points: perlin is NULL");
@@ -986,11 +1066,12 @@ extern "C" int wn_perlin_points(const wn_perlin *pn, const float *p, size_t coun
     wn_ctx *c = pn->ctx;
     DeviceGuard g(c->device);
     const int32_t *perm = pn->d;
+    const int fast = pn->fast;
     if (space == WN_DEVICE)
-        return run_device(c, [&](cudaStream_t st) { return wn_launch_perlin_points(perm, WnPointsAoS{p, pre}, 0, count, out, st); });
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_perlin_points(perm, WnPointsAoS{p, pre}, 0, count, out, fast, st); });
     ChunkIO io; io.in = p; io.in_item = 3 * sizeof(float); io.out = out;
     return run_chunked_host(c, count, kChunkSamples, io, [&](void *din, void *, float *dout, size_t, size_t cnt, cudaStream_t st) {
-        return wn_launch_perlin_points(perm, WnPointsAoS{(const float *)din, pre}, 0, cnt, dout, st);
+        return wn_launch_perlin_points(perm, WnPointsAoS{(const float *)din, pre}, 0, cnt, dout, fast, st);
     });
 }
 
@@ -1014,11 +1095,12 @@ extern "C" int wn_perlin_lattice(const wn_perlin *pn, const float *xs, int nx, c
     if ((r = pw.put(zs, nz * sizeof(float), (const void **)&L.zs))) return r;
     if ((r = pw.flush())) return r;
     const int32_t *perm = pn->d;
+    const int fast = pn->fast;
     if (space == WN_DEVICE)
-        return run_device(c, [&](cudaStream_t st) { return wn_launch_perlin_lattice(perm, L, 0, total, out, st); });
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_perlin_lattice(perm, L, 0, total, out, fast, st); });
     ChunkIO io; io.out = out;
     return run_chunked_host(c, total, kChunkSamples, io, [&](void *, void *, float *dout, size_t first, size_t cnt, cudaStream_t st) {
-        return wn_launch_perlin_lattice(perm, L, first, cnt, dout, st);
+        return wn_launch_perlin_lattice(perm, L, first, cnt, dout, fast, st);
     });
 }
 
@@ -1037,11 +1119,12 @@ extern "C" int wn_perlin_grid(const wn_perlin *pn, const float origin[3], const 
     if (!total) return WN_OK;
     WN_REQUIRE(out, "wn_perlin_grid: out is NULL");
     const int32_t *perm = pn->d;
+    const int fast = pn->fast;
     if (space == WN_DEVICE)
-        return run_device(c, [&](cudaStream_t st) { return wn_launch_perlin_affine(perm, A, 0, total, out, st); });
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_perlin_affine(perm, A, 0, total, out, fast, st); });
     ChunkIO io; io.out = out;
     return run_chunked_host(c, total, kChunkSamples, io, [&](void *, void *, float *dout, size_t first, size_t cnt, cudaStream_t st) {
-        return wn_launch_perlin_affine(perm, A, first, cnt, dout, st);
+        return wn_launch_perlin_affine(perm, A, first, cnt, dout, fast, st);
     });
 }
 

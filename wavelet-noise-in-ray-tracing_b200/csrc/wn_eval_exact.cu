@@ -222,6 +222,35 @@ __device__ double perlin3(const int *p /* 512 ints, shared memory */, double x, 
                  plerp(u, pgrad(p[AB + 1], x, y1, z1), pgrad(p[BB + 1], x1, y1, z1))));
 }
 
+// ---- Perlin, single precision (fast mode, opt-in) -----------------------------------------------------
+// The same algorithm in FP32 with FMAs: every reference caller passes float-valued coordinates, so x - floor(x) is
+// exact in FP32 too and the result differs from the FP64 kernel by rounding only (tests bound it by 1e-5 * range 2).
+// The float selects of grad() are single ALU ops where the FP64 ones are two, and the arithmetic leaves the FP64 pipe.
+__device__ __forceinline__ float pfadef(float t) { return t * t * t * fmaf(t, fmaf(t, 6.0f, -15.0f), 10.0f); }
+__device__ __forceinline__ float plerpf(float t, float a, float b) { return fmaf(t, b - a, a); }
+__device__ __forceinline__ float pgradf(int hash, float x, float y, float z)
+{
+    const int h = hash & 15;
+    const float u = h < 8 ? x : y;
+    const float v = h < 4 ? y : ((h == 12 || h == 14) ? x : z);
+    return ((h & 1) == 0 ? u : -u) + ((h & 2) == 0 ? v : -v);
+}
+__device__ float perlin3f(const int *p, float x, float y, float z)
+{
+    const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    const int X = (int)fx & 255, Y = (int)fy & 255, Z = (int)fz & 255;
+    x -= fx; y -= fy; z -= fz;
+    const float u = pfadef(x), v = pfadef(y), w = pfadef(z);
+    const int A = p[X] + Y, AA = p[A] + Z, AB = p[A + 1] + Z;
+    const int B = p[X + 1] + Y, BA = p[B] + Z, BB = p[B + 1] + Z;
+    const float x1 = x - 1.0f, y1 = y - 1.0f, z1 = z - 1.0f;
+    return plerpf(w,
+        plerpf(v, plerpf(u, pgradf(p[AA], x, y, z),      pgradf(p[BA], x1, y, z)),
+                  plerpf(u, pgradf(p[AB], x, y1, z),     pgradf(p[BB], x1, y1, z))),
+        plerpf(v, plerpf(u, pgradf(p[AA + 1], x, y, z1), pgradf(p[BA + 1], x1, y, z1)),
+                  plerpf(u, pgradf(p[AB + 1], x, y1, z1), pgradf(p[BB + 1], x1, y1, z1))));
+}
+
 // ---- coordinate generators -------------------------------------------------------------------------
 __device__ __forceinline__ void coord2(const WnPointsAoS &c, size_t s, float p[3])
 {
@@ -285,7 +314,7 @@ __global__ void k_proj(WnTileView t, C c, const float *normals, float n0, float 
     if (normals) { nrm[0] = __ldg(normals + 3 * s); nrm[1] = __ldg(normals + 3 * s + 1); nrm[2] = __ldg(normals + 3 * s + 2); }
     out[s] = FMUL(eval3d_projected(t, p, nrm), post);
 }
-template <class C>
+template <class C, bool FAST>
 __global__ void k_perlin(const int32_t *perm, C c, size_t first, size_t count, float *out)
 {
     __shared__ int sp[512];
@@ -294,7 +323,18 @@ __global__ void k_perlin(const int32_t *perm, C c, size_t first, size_t count, f
     WN_TID_OR_RETURN(count);
     float p[3];
     coord(c, first + s, p);
-    out[s] = (float)perlin3(sp, (double)p[0], (double)p[1], (double)p[2]);
+    if (FAST) out[s] = perlin3f(sp, p[0], p[1], p[2]);
+    else out[s] = (float)perlin3(sp, (double)p[0], (double)p[1], (double)p[2]);
+}
+// double coordinates in, double noise out: PerlinNoise::noise(double, double, double) as declared
+// (experient/PerlinNoise.hpp:36, perlin.h:42) for callers whose coordinates are not float-valued
+__global__ void k_perlin_f64(const int32_t *perm, const double *p, size_t count, double *out)
+{
+    __shared__ int sp[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sp[i] = perm[i];
+    __syncthreads();
+    WN_TID_OR_RETURN(count);
+    out[s] = perlin3(sp, p[3 * s], p[3 * s + 1], p[3 * s + 2]);
 }
 
 // texture.h:67-107 (3D branch).  oct2 = octave_scale * 2.0f (float), inv_std = 1.0f/sqrt(0.18402f)
@@ -423,22 +463,31 @@ int wn_launch_proj_affine(WnTileView t, WnAffine c, const float nrm[3], size_t f
     k_proj<WnAffine><<<blocks_for(count, 128), 128, 0, st>>>(t, c, nullptr, nrm[0], nrm[1], nrm[2], first, count, post, out);
     return 1;
 }
-int wn_launch_perlin_points(const int32_t *perm, WnPointsAoS c, size_t first, size_t count, float *out, cudaStream_t st)
+int wn_launch_perlin_points(const int32_t *perm, WnPointsAoS c, size_t first, size_t count, float *out, int fast, cudaStream_t st)
 {
     if (!count) return 0;
-    k_perlin<WnPointsAoS><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
+    if (fast) k_perlin<WnPointsAoS, true><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
+    else k_perlin<WnPointsAoS, false><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
     return 1;
 }
-int wn_launch_perlin_lattice(const int32_t *perm, WnLattice c, size_t first, size_t count, float *out, cudaStream_t st)
+int wn_launch_perlin_lattice(const int32_t *perm, WnLattice c, size_t first, size_t count, float *out, int fast, cudaStream_t st)
 {
     if (!count) return 0;
-    k_perlin<WnLattice><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
+    if (fast) k_perlin<WnLattice, true><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
+    else k_perlin<WnLattice, false><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
     return 1;
 }
-int wn_launch_perlin_affine(const int32_t *perm, WnAffine c, size_t first, size_t count, float *out, cudaStream_t st)
+int wn_launch_perlin_affine(const int32_t *perm, WnAffine c, size_t first, size_t count, float *out, int fast, cudaStream_t st)
 {
     if (!count) return 0;
-    k_perlin<WnAffine><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
+    if (fast) k_perlin<WnAffine, true><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
+    else k_perlin<WnAffine, false><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
+    return 1;
+}
+int wn_launch_perlin_points_f64(const int32_t *perm, const double *p, size_t count, double *out, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_perlin_f64<<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, p, count, out);
     return 1;
 }
 int wn_launch_wavelet_texture(WnTileView t, const float *p, size_t count, double scale, float oct2, float inv_std,

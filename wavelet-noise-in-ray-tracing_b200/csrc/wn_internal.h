@@ -41,6 +41,12 @@ struct WnTileView {
     const float *Npad;          // 3D only: rows padded to n+WN_TILE_PAD floats, the extra cells wrap around (fast lattice kernel)
 };
 
+// ---- stream-ordered scratch (wn_capi.cu) ------------------------------------------------------------
+// Filter temporaries, MT19937 draws, axis tables and period blocks come from a memory pool PRIVATE to this library
+// (one per device, release threshold = keep): recycled across calls like the default pool would, without touching the
+// attributes of the device's default pool that the host application (torch, ...) may be using.  Free with cudaFreeAsync.
+cudaError_t wn_scratch_alloc(void **p, size_t bytes, cudaStream_t st);
+
 // ---- tile construction (wn_tilegen.cu) ------------------------------------------------------------
 // dst = filter_axis(src) for axis in {0,1,2}; when minuend != nullptr: dst = minuend - filter_axis(src).
 // tmp smem sizes are handled inside.  Returns the number of kernels launched.
@@ -60,9 +66,11 @@ int wn_launch_proj_points(WnTileView t, WnPointsAoS c, const float *normals, con
                           size_t count, float post, float *out, cudaStream_t st);
 int wn_launch_proj_affine(WnTileView t, WnAffine c, const float nrm[3], size_t first, size_t count, float post,
                           float *out, cudaStream_t st);
-int wn_launch_perlin_points(const int32_t *perm, WnPointsAoS c, size_t first, size_t count, float *out, cudaStream_t st);
-int wn_launch_perlin_lattice(const int32_t *perm, WnLattice c, size_t first, size_t count, float *out, cudaStream_t st);
-int wn_launch_perlin_affine(const int32_t *perm, WnAffine c, size_t first, size_t count, float *out, cudaStream_t st);
+// fast != 0: FP32 arithmetic with FMAs (<= 1e-5 * range of the FP64 kernel), else the reference's FP64 un-fused order
+int wn_launch_perlin_points(const int32_t *perm, WnPointsAoS c, size_t first, size_t count, float *out, int fast, cudaStream_t st);
+int wn_launch_perlin_lattice(const int32_t *perm, WnLattice c, size_t first, size_t count, float *out, int fast, cudaStream_t st);
+int wn_launch_perlin_affine(const int32_t *perm, WnAffine c, size_t first, size_t count, float *out, int fast, cudaStream_t st);
+int wn_launch_perlin_points_f64(const int32_t *perm, const double *p, size_t count, double *out, cudaStream_t st);
 // texture hooks: scale (double) and octave as in texture.h
 int wn_launch_wavelet_texture(WnTileView t, const float *p, size_t count, double scale, float oct2, float inv_std,
                               float *grey, cudaStream_t st);

@@ -28,6 +28,8 @@
 //   * The launches of a call are chained with programmatic dependent launch (chain_wait / chain_release).
 #include "wn_internal.h"
 
+#include <cuda.h>                 // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -737,6 +739,403 @@ k_mb3d_col4(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int
     }
 }
 
+// ---- k_mb3d_rep: k_mb3d_col4 with the period-block value shared between replicas -------------------------------------
+// The main kernel is bound by data movement, not arithmetic: every sample costs one period-block read (through L2)
+// and one output write.  Samples that are a whole number of period blocks apart read the SAME period-block value, so a
+// thread here owns R = RX * RY of them: sample (i, j, k) of the "base region" [0, bx) x [0, by) and its replicas
+// (i + qx*bx, j + qy*by, k).  The period-block value is fetched once per R outputs (L2 -> SM traffic, ring fill and
+// read-back divided by R), the z-table entry and the window bookkeeping are shared too.
+//   * Host guarantee (plan_replicas): for every direct band the axis-table entries at i and i + bx carry bit-identical
+//     weights and first tap cells that differ by a constant (cxs[b] cells; cys[b] along y).  A replica is then the same
+//     computation on a tile shifted by that many cells: own rows of U (X pass), own 3-deep window, same weights.
+//   * Thread mapping: a warp covers 32/YPW float4 columns x YPW y rows.  With YPW = 4 the lanes of a warp that share
+//     x read the same U rows while a band advances less than one cell per y sample, so a window advance costs one
+//     shared-memory wavefront instead of four; stores stay whole 128-byte lines (32 samples per row and warp).
+//   * Arithmetic: the same operations in the same order as k_mb3d_col4 / brick4 / brick (bit-identical samples), issued
+//     as packed pairs (FFMA2 / FMUL2 / FADD2, sm_100): half the issue slots for the same IEEE results.
+//   * Period-block ring, RINGMODE 0: per-thread cp.async slots as in k_mb3d_col4 (any brick, any period block).
+//     RINGMODE 1: one elected thread fetches the CTA's 128 x 8 x 4 sub-box of the period block with ONE TMA tensor copy
+//     (cp.async.bulk.tensor.3d, 16 KB) per four z planes into one half of an 8-plane ring; full/empty mbarriers per
+//     half, consumers wait once per four planes and the LSU pipe carries no fill traffic.  Needs whole bricks and a
+//     period block whose edges are multiples of the box (checked by the host).
+struct WnRep {
+    int bx, by;                 // base region in samples; the grid covers it, replica (qx, qy) adds (qx*bx, qy*by)
+    int cxs[2], cys[2];         // per direct band: first-tap-cell shift of one replica step along x / y
+    long long roff[4];          // byte offset of replica r = qy*RX + qx in the output: 4 * (qx*bx + nx*qy*by)
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WN_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra WN_DONE;\n"
+        "bra WN_WAIT;\n"
+        "WN_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one 3D box of the period block -> shared memory; completion is signalled on `bar` (complete_tx)
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int x, int y, int z, unsigned long long *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// packed forms of q4_ycontract / q4_band_value / q4_band_add: the same IEEE operations, two lanes per instruction
+__device__ __forceinline__ float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float4 cat4(const float2 a, const float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
+__device__ __forceinline__ float4 p4_contract3(const float w0, const float w1, const float w2, const float4 a0, const float4 a1,
+                                               const float4 a2)
+{
+    // per component: fmaf(w2, a2, fmaf(w1, a1, w0 * a0))
+    const float2 s0 = make_float2(w0, w0), s1 = make_float2(w1, w1), s2 = make_float2(w2, w2);
+    const float2 l = __ffma2_rn(s2, lo2(a2), __ffma2_rn(s1, lo2(a1), __fmul2_rn(s0, lo2(a0))));
+    const float2 h = __ffma2_rn(s2, hi2(a2), __ffma2_rn(s1, hi2(a1), __fmul2_rn(s0, hi2(a0))));
+    return cat4(l, h);
+}
+__device__ __forceinline__ float4 p4_band_value(const float4 tz, const float4 (&v)[3])
+{
+    // per component: fmaf(tz.x, v0, fmaf(tz.y, v1, tz.z * v2))  == band_value()
+    return p4_contract3(tz.z, tz.y, tz.x, v[2], v[1], v[0]);
+}
+__device__ __forceinline__ float4 p4_add(const float4 a, const float4 b)
+{
+    return cat4(__fadd2_rn(lo2(a), lo2(b)), __fadd2_rn(hi2(a), hi2(b)));
+}
+
+// footprints of all bands with R replicas each: band b owns U rows [row0[b], row0[b+1]) = R blocks of rows2 rows, the
+// block of replica r = qy*RX + qx holds the tile rows shifted by qy*cys[b] cells in y (the x shift is applied by the X
+// pass); ends with a barrier
+template <int BY, int BZ, int NT, int RX, int RY, int NSH, bool POW2>
+__device__ __forceinline__ void q4_footprints_rep(const float4 *s_tab, int nbands, int n, Q4Foot &ft, int *s_rowoff,
+                                                  const WnRep &rep)
+{
+    constexpr int BX = 128, PER_BAND = BX + BY + BZ, pow2 = POW2 ? 1 : 0, R = RX * RY;
+    // the last NSH bands are SHARED: their replicas coincide (cell shift = a whole number of tile periods), one block
+    const int pitch = n + WN_TILE_PAD;
+    if (threadIdx.x == 0) {
+        int row0 = 0;
+        for (int b = 0; b < nbands; ++b) {
+            const float4 *tY = s_tab + b * PER_BAND + BX, *tZ = tY + BY;
+            const int ey = __float_as_int(tY[BY - 1].w) - __float_as_int(tY[0].w) + 3;
+            const int ez = __float_as_int(tZ[BZ - 1].w) - __float_as_int(tZ[0].w) + 3;
+            ft.ey[b] = ey; ft.ez[b] = ez; ft.row0[b] = row0;
+            row0 += (b >= nbands - NSH ? 1 : R) * ((ey * ez + 1) & ~1);
+        }
+        ft.row0[nbands] = row0;
+    }
+    __syncthreads();
+    for (int b = 0; b < nbands; ++b) {
+        const float4 *tY = s_tab + b * PER_BAND + BX, *tZ = tY + BY;
+        const int my0 = __float_as_int(tY[0].w), mz0 = __float_as_int(tZ[0].w);
+        const int Ey = ft.ey[b], rows = Ey * ft.ez[b], rows2 = (rows + 1) & ~1, row0 = ft.row0[b];
+        const float inv_ey = 1.0f / (float)Ey;
+        const bool shared = b >= nbands - NSH;
+        for (int r = threadIdx.x; r < rows2; r += NT) {
+            const int rr = min(r, rows - 1);
+            const int cz = (int)(((float)rr + 0.5f) * inv_ey), cy = rr - cz * Ey;       // exact for rows < 2^20
+            const int zoff = tmodf(mz0 + cz, n, pow2) * n;
+            if (shared) { s_rowoff[row0 + r] = (zoff + tmodf(my0 + cy, n, pow2)) * pitch; continue; }
+#pragma unroll
+            for (int qy = 0; qy < RY; ++qy) {
+                const int off = (zoff + tmodf(my0 + cy + qy * rep.cys[b], n, pow2)) * pitch;
+#pragma unroll
+                for (int qx = 0; qx < RX; ++qx) s_rowoff[row0 + (qy * RX + qx) * rows2 + r] = off;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// X pass of one band for all its replicas: rows [row0, row0 + R*rows2), replica r = (row - row0) / rows2 reads the tile
+// shifted by (r % RX) * cxs cells in x.  Same arithmetic as q4_xpass.
+template <int NT, int RX, int RY, bool POW2>
+__device__ __forceinline__ void q4_xpass_rep(const float *__restrict__ N, int n, const float4 *tX, float4 *U4,
+                                             const int *s_rowoff, int row0, int rows2, int cxs)
+{
+    constexpr int NW = NT / 32, pow2 = POW2 ? 1 : 0, R = RX * RY;
+    static_assert(RX == 1 || RX == 2, "x replicas: 1 or 2");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4 t0 = tX[lane], t1 = tX[32 + lane], t2 = tX[64 + lane], t3 = tX[96 + lane];
+    const int c0 = __float_as_int(t0.w), c1 = __float_as_int(t1.w), c2 = __float_as_int(t2.w), c3 = __float_as_int(t3.w);
+    const int cmin = min(min(c0, c1), min(c2, c3)), cmax = max(max(c0, c1), max(c2, c3));
+    const bool narrow = __all_sync(0xffffffffu, cmax - cmin <= 1);
+    const int half = rows2 >> 1, pairs = half * R;
+    if (narrow) {
+        const float *base0 = N + tmodf(cmin, n, pow2);
+        const float *base1 = N + tmodf(cmin + cxs, n, pow2);
+        const bool s0 = c0 != cmin, s1 = c1 != cmin, s2 = c2 != cmin, s3 = c3 != cmin;
+        const float a00 = s0 ? 0.0f : t0.x, a01 = s0 ? t0.x : t0.y, a02 = s0 ? t0.y : t0.z, a03 = s0 ? t0.z : 0.0f;
+        const float a10 = s1 ? 0.0f : t1.x, a11 = s1 ? t1.x : t1.y, a12 = s1 ? t1.y : t1.z, a13 = s1 ? t1.z : 0.0f;
+        const float a20 = s2 ? 0.0f : t2.x, a21 = s2 ? t2.x : t2.y, a22 = s2 ? t2.y : t2.z, a23 = s2 ? t2.z : 0.0f;
+        const float a30 = s3 ? 0.0f : t3.x, a31 = s3 ? t3.x : t3.y, a32 = s3 ? t3.y : t3.z, a33 = s3 ? t3.z : 0.0f;
+        for (int p = warp; p < pairs; p += NW) {
+            const int rr = (p >= half) + (R > 2 ? (p >= 2 * half) + (p >= 3 * half) : 0);
+            const float *base = (RX == 2 && (rr & 1)) ? base1 : base0;
+            const int r = row0 + 2 * p;
+            const int2 o = *reinterpret_cast<const int2 *>(s_rowoff + r);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float *q = base + (unsigned)(h ? o.y : o.x);
+                const float v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
+                float4 u;
+                u.x = fmaf(a03, v3, fmaf(a02, v2, fmaf(a01, v1, a00 * v0)));
+                u.y = fmaf(a13, v3, fmaf(a12, v2, fmaf(a11, v1, a10 * v0)));
+                u.z = fmaf(a23, v3, fmaf(a22, v2, fmaf(a21, v1, a20 * v0)));
+                u.w = fmaf(a33, v3, fmaf(a32, v2, fmaf(a31, v1, a30 * v0)));
+                U4[(r + h) * 32 + lane] = u;
+            }
+        }
+    } else {
+        for (int p = warp; p < pairs; p += NW) {
+            const int rr = (p >= half) + (R > 2 ? (p >= 2 * half) + (p >= 3 * half) : 0);
+            const int sh = (RX == 2 && (rr & 1)) ? cxs : 0;
+            const float *b0 = N + tmodf(c0 + sh, n, pow2), *b1 = N + tmodf(c1 + sh, n, pow2);
+            const float *b2 = N + tmodf(c2 + sh, n, pow2), *b3 = N + tmodf(c3 + sh, n, pow2);
+            const int r = row0 + 2 * p;
+            const int2 o = *reinterpret_cast<const int2 *>(s_rowoff + r);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const unsigned off = (unsigned)(h ? o.y : o.x);
+                const float *q0 = b0 + off, *q1 = b1 + off, *q2 = b2 + off, *q3 = b3 + off;
+                float4 u;
+                u.x = fmaf(t0.z, __ldg(q0 + 2), fmaf(t0.y, __ldg(q0 + 1), t0.x * __ldg(q0)));
+                u.y = fmaf(t1.z, __ldg(q1 + 2), fmaf(t1.y, __ldg(q1 + 1), t1.x * __ldg(q1)));
+                u.z = fmaf(t2.z, __ldg(q2 + 2), fmaf(t2.y, __ldg(q2 + 1), t2.x * __ldg(q2)));
+                u.w = fmaf(t3.z, __ldg(q3 + 2), fmaf(t3.y, __ldg(q3 + 1), t3.x * __ldg(q3)));
+                U4[(r + h) * 32 + lane] = u;
+            }
+        }
+    }
+}
+
+constexpr int rep_min_blocks(int windows) { return windows <= 2 ? 3 : 2; }
+
+// NB direct bands; the last NSH of them are shared by the replicas (see q4_footprints_rep), the others have one window
+// per replica
+template <int NB, int NSH, int RX, int RY, int YPW, int RINGMODE, bool POW2>
+__global__ void __launch_bounds__(256, rep_min_blocks((NB - NSH) * RX * RY + NSH))
+k_mb3d_rep(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int nk, int max_rows, WnFold fold,
+           WnOrder ord, WnRep rep, const __grid_constant__ CUtensorMap pmap, float *__restrict__ out)
+{
+    constexpr int BX = 128, BY = 8, BZ = 32, NT = 256, R = RX * RY;
+    constexpr int RING = NB == 1 ? 8 : 4;                       // period-block planes in flight (two bands: U needs the room)
+    constexpr int HP = RING / 2;                                // RINGMODE 1: planes per TMA box = half a ring
+    constexpr int PER_BAND = BX + BY + BZ;
+    constexpr int LPR = 32 / YPW;                               // lanes per y row of a warp
+    static_assert(YPW == 1 || YPW == 2 || YPW == 4, "y rows per warp");
+    static_assert(NB >= 1 && NB <= 2 && NSH >= 0 && NSH < NB && R <= 4, "windows live in registers");
+    constexpr int NR = NB - NSH;                                 // bands [0, NR) have a window per replica
+    const bool folded = fold.P != nullptr;
+    // dynamic shared memory (float4 units): [ring RING x NT, only when folded] | U[max_rows][32] | tables NB x PER_BAND |
+    // rowoff[max_rows] (int) | mbarriers
+    extern __shared__ __align__(128) float4 smem_rep[];
+    float4 *ringbuf = smem_rep;
+    float4 *U4 = smem_rep + (folded ? RING * NT : 0);
+    float4 *s_tab = U4 + max_rows * 32;
+    int *s_rowoff = reinterpret_cast<int *>(s_tab + NB * PER_BAND);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(s_rowoff + max_rows);   // full[2], empty[2]
+
+    chain_wait();                                              // the ring prefetch below reads the previous kernel's output
+    chain_release();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int yb, zb;
+    {
+        const int gy = blockIdx.y, rz = gy % ord.zrep, t = gy / ord.zrep;
+        yb = t / ord.yrep + (t % ord.yrep) * ord.yper;
+        zb = rz * ord.zper + blockIdx.z;
+    }
+    const int i0 = blockIdx.x * BX, j0 = yb * BY, k0 = zb * BZ;
+    const int xq = (warp % YPW) * LPR + (lane % LPR);            // float4 column of this thread in the 128-sample row
+    const int jl = (warp / YPW) * YPW + lane / LPR;              // y row of this thread in the brick
+    const int i = i0 + 4 * xq, j = j0 + jl;
+    const bool active = i < rep.bx && j < rep.by;
+    const int kmax = min(BZ, nk - k0);
+
+    // ---- period-block prefetch (before the tables and the X pass)
+    const size_t pplane = (size_t)fold.Lx * fold.Ly;
+    const float *pcol = nullptr, *pp = nullptr;
+    int kk = 0;
+    float4 *ring = ringbuf + threadIdx.x;                        // RINGMODE 0: this thread's private slots
+    int tma_x = 0, tma_y = 0, tma_z = 0;
+    if (folded) {
+        kk = fold.kphase + k0;
+        if (kk >= fold.Lz) kk %= fold.Lz;
+        if constexpr (RINGMODE == 1) {
+            if (threadIdx.x == 0) {
+                tma_x = fold.xmask >= 0 ? (i0 & fold.xmask) : i0 % fold.Lx;
+                tma_y = fold.ymask >= 0 ? (j0 & fold.ymask) : j0 % fold.Ly;
+                tma_z = kk;
+                mbar_init(bars + 0, 1); mbar_init(bars + 1, 1);
+                mbar_init(bars + 2, NT / 32); mbar_init(bars + 3, NT / 32);
+                mbar_fence_init();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    mbar_arrive_expect_tx(bars + h, HP * BY * BX * (unsigned)sizeof(float));
+                    tma_load_3d(ringbuf + h * HP * NT, &pmap, tma_x, tma_y, tma_z, bars + h);
+                    tma_z += HP;
+                    if (tma_z >= fold.Lz) tma_z -= fold.Lz;
+                }
+            }
+        } else if (active) {
+            const unsigned pi = (unsigned)(fold.xmask >= 0 ? (i & fold.xmask) : i % fold.Lx);
+            const unsigned pj = (unsigned)(fold.ymask >= 0 ? (j & fold.ymask) : j % fold.Ly);
+            pcol = fold.P + (pi + pj * (unsigned)fold.Lx);
+            pp = pcol + kk * pplane;
+#pragma unroll
+            for (int d = 0; d < RING - 1; ++d) {
+                if (d < kmax) {
+                    cp_async16(ring + d * NT, pp);
+                    if (++kk == fold.Lz) { kk = 0; pp = pcol; } else pp += pplane;
+                }
+                cp_async_commit();
+            }
+        }
+    }
+
+    // clamped at the base region: the footprints then match the host's plan (plan_bricks over [0, by))
+    q4_load_tables<BY, BZ, NT>(s_tab, tabs, i0, j0, k0, rep.bx, rep.by, nk);
+    __shared__ Q4Foot ft;
+    q4_footprints_rep<BY, BZ, NT, RX, RY, NSH, POW2>(s_tab, NB, n, ft, s_rowoff, rep);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        if (b < NR)
+            q4_xpass_rep<NT, RX, RY, POW2>(N, n, s_tab + b * PER_BAND, U4, s_rowoff, ft.row0[b],
+                                           (ft.row0[b + 1] - ft.row0[b]) / R, rep.cxs[b]);
+        else
+            q4_xpass_rep<NT, 1, 1, POW2>(N, n, s_tab + b * PER_BAND, U4, s_rowoff, ft.row0[b], ft.row0[b + 1] - ft.row0[b], 0);
+    }
+    __syncthreads();
+    if (RINGMODE == 0 && !active) return;                      // no barrier below (RINGMODE 1 runs on whole bricks only)
+
+    // per band: y weights, per replica the 3-deep window of y-contracted tile-z planes, the next plane to contract
+    float4 ty[NB], v[NB][R][3];
+    const float4 *unext[NB], *tZ[NB];
+    int slab4[NB], rstride[NB], mz0[NB], base[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const float4 *tY = s_tab + b * PER_BAND + BX;
+        tZ[b] = tY + BY;
+        ty[b] = tY[jl];
+        slab4[b] = ft.ey[b] * 32;
+        rstride[b] = b < NR ? (ft.row0[b + 1] - ft.row0[b]) / R * 32 : 0;
+        mz0[b] = __float_as_int(tZ[b][0].w);
+        const float4 *u = U4 + ft.row0[b] * 32 + (__float_as_int(ty[b].w) - __float_as_int(tY[0].w)) * 32 + xq;
+#pragma unroll
+        for (int r = 0; r < (b < NR ? R : 1); ++r)
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                const float4 *uu = u + r * rstride[b] + f * slab4[b];
+                v[b][r][f] = p4_contract3(ty[b].x, ty[b].y, ty[b].z, uu[0], uu[32], uu[64]);
+            }
+        unext[b] = u + 3 * slab4[b];
+        base[b] = 0;
+    }
+
+    const size_t plane = (size_t)nx * ny;
+    float *o = out + ((size_t)i + (size_t)nx * j + plane * k0);
+    // one z step: advance the windows, then finish the R samples of this thread (canonical sum: period-block value or
+    // 0 first, then the bands from the highest scale down, each band value formed from zero)
+    auto zstep_a = [&](int k, float4 (&tz)[NB]) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            tz[b] = tZ[b][k];
+            const int rel = __float_as_int(tz[b].w) - mz0[b];
+#pragma unroll 1
+            while (base[b] < rel) {
+                ++base[b];
+#pragma unroll
+                for (int r = 0; r < (b < NR ? R : 1); ++r) {
+                    const float4 *uu = unext[b] + r * rstride[b];
+                    const float4 nv = p4_contract3(ty[b].x, ty[b].y, ty[b].z, uu[0], uu[32], uu[64]);
+                    v[b][r][0] = v[b][r][1]; v[b][r][1] = v[b][r][2]; v[b][r][2] = nv;
+                }
+                unext[b] += slab4[b];
+            }
+        }
+    };
+    auto zstep_b = [&](const float4 (&tz)[NB], const float4 pv) {
+        float4 sh = pv;                                        // shared bands: the same value for every replica
+#pragma unroll
+        for (int b = NB - 1; b >= NR; --b) sh = p4_add(p4_band_value(tz[b], v[b][0]), sh);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float4 s = sh;
+#pragma unroll
+            for (int b = NR - 1; b >= 0; --b) s = p4_add(p4_band_value(tz[b], v[b][r]), s);
+            __stcs(reinterpret_cast<float4 *>(reinterpret_cast<char *>(o) + rep.roff[r]), s);
+        }
+        o += plane;
+    };
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (!folded) {
+        for (int k = 0; k < kmax; ++k) {
+            float4 tz[NB];
+            zstep_a(k, tz);
+            zstep_b(tz, zero4);
+        }
+    } else if constexpr (RINGMODE == 1) {
+        const float4 *mine = ringbuf + jl * 32 + xq;              // plane layout [8 y][128 x]
+#pragma unroll 1
+        for (int g = 0; g < BZ / HP; ++g) {                      // one group = one TMA box = HP planes
+            const int h = g & 1;
+            const unsigned par = (unsigned)(g >> 1) & 1u;
+            bool waited = false;
+#pragma unroll
+            for (int d = 0; d < HP; ++d) {
+                float4 tz[NB];
+                zstep_a(g * HP + d, tz);
+                if (!waited) { mbar_wait(bars + h, par); waited = true; }
+                zstep_b(tz, mine[(h * HP + d) * NT]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 2 + h);
+            if (threadIdx.x == 0 && g + 2 < BZ / HP) {            // refill this half with the planes two groups ahead
+                mbar_wait(bars + 2 + h, par);
+                mbar_arrive_expect_tx(bars + h, HP * BY * BX * (unsigned)sizeof(float));
+                tma_load_3d(ringbuf + h * HP * NT, &pmap, tma_x, tma_y, tma_z, bars + h);
+                tma_z += HP;
+                if (tma_z >= fold.Lz) tma_z -= fold.Lz;
+            }
+        }
+    } else {
+#pragma unroll 4
+        for (int k = 0; k < kmax; ++k) {
+            float4 tz[NB];
+            zstep_a(k, tz);
+            if (k + RING - 1 < kmax) {                         // slot of plane k-1, consumed in the previous step
+                cp_async16(ring + ((k + RING - 1) % RING) * NT, pp);
+                if (++kk == fold.Lz) { kk = 0; pp = pcol; } else pp += pplane;
+            }
+            cp_async_commit();
+            cp_async_wait<RING - 1>();                         // plane k has landed
+            zstep_b(tz, ring[(k % RING) * NT]);
+        }
+    }
+}
+
 __global__ void k_pad_tile(const float *__restrict__ N, float *__restrict__ P, int n)
 {
     const int pitch = n + WN_TILE_PAD;
@@ -814,6 +1213,7 @@ struct HostAxes {
     const HostEntry *ex(int row) const { return e.data() + row * per_band(); }
     const HostEntry *ey(int row) const { return ex(row) + nx; }
     const HostEntry *ez(int row) const { return ey(row) + ny; }
+    const int *fx(int row) const { return first.data() + row * per_band(); }
     const int *fy(int row) const { return first.data() + row * per_band() + nx; }
     const int *fz(int row) const { return fy(row) + ny; }
 };
@@ -998,6 +1398,142 @@ int launch_col4(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk,
     return 1;
 }
 
+// ---- replica kernel (k_mb3d_rep): host side ----------------------------------------------------------------------
+// Two halves of an axis are replicas of each other for a band when entry i + S carries bit-identical weights and a
+// first tap cell that differs from entry i's by one constant, for every i in [0, S) (S = len / 2).
+bool axis_replica_shift(const HostEntry *e, const int *first, int len, int *shift)
+{
+    if (len < 2 || (len & 1)) return false;
+    const int S = len / 2, c = first[S] - first[0];
+    for (int i = 0; i < S; ++i)
+        if (std::memcmp(&e[i].w0, &e[i + S].w0, 3 * sizeof(float)) != 0 || first[i + S] - first[i] != c) return false;
+    *shift = c;
+    return true;
+}
+
+// tensor map of the period block float32[Lz][Ly][Lx] with a 128 x 8 x planes box (one half of the kernel's ring)
+bool make_period_map(const float *P, int Lx, int Ly, int Lz, int planes, CUtensorMap *map)
+{
+    typedef CUresult (*Encode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const Encode encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            fn = nullptr;
+        }
+        return reinterpret_cast<Encode>(fn);
+    }();
+    if (!encode) return false;
+    const cuuint64_t dims[3] = { (cuuint64_t)Lx, (cuuint64_t)Ly, (cuuint64_t)Lz };
+    const cuuint64_t strides[2] = { (cuuint64_t)Lx * sizeof(float), (cuuint64_t)Lx * Ly * sizeof(float) };
+    const cuuint32_t box[3] = { 128, 8, (cuuint32_t)planes }, estr[3] = { 1, 1, 1 };
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(P), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NB, int NSH, int RX, int RY, int YPW, int RINGMODE>
+int launch_rep(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk, float *out, int max_rows, size_t smem, WnFold fold,
+               const WnRep &rep, const CUtensorMap &pmap, cudaStream_t st)
+{
+    constexpr int BY = 8, BZ = 32, NT = 256;
+    auto kern = t.pow2 ? k_mb3d_rep<NB, NSH, RX, RY, YPW, RINGMODE, true> : k_mb3d_rep<NB, NSH, RX, RY, YPW, RINGMODE, false>;
+    if (!allow_smem(kern, smem)) return -1;
+    const int nyb = (rep.by + BY - 1) / BY, nzb = (nk + BZ - 1) / BZ;
+    WnOrder ord{1, nyb, 1, nzb};
+    bool replica = fold.P && (long long)fold.Lx * fold.Ly * fold.Lz > (8LL << 20);
+    if (const char *e = getenv("WN_REPLICA_ORDER")) replica = fold.P && atoi(e) != 0;
+    if (replica) {
+        if (fold.Ly % BY == 0 && rep.by % fold.Ly == 0) { ord.yrep = rep.by / fold.Ly; ord.yper = fold.Ly / BY; }
+        if (fold.kphase == 0 && fold.Lz % BZ == 0 && nk % fold.Lz == 0 && (long long)nyb * (nk / fold.Lz) <= 65535) {
+            ord.zrep = nk / fold.Lz; ord.zper = fold.Lz / BZ;
+        }
+    }
+    dim3 grid((rep.bx + 127) / 128, nyb * ord.zrep, ord.zper);
+    launch_chained(tabs.pdl != 0, kern, grid, dim3(NT), smem, st, t.Npad, t.n, tabs, nx, ny, nk, max_rows, fold, ord, rep, pmap, out);
+    return 1;
+}
+
+// Replica kernel for a lattice window with one or two direct bands.  Returns kernels launched, 0 when the window does
+// not qualify (the caller falls back to k_mb3d_col4), -1 on a launch error.
+// Knobs (A/B runs): WN_REP=0 off, "11" / "12" / "22" = at most that many replicas along x and y (default "22");
+// WN_REP_YPW=1|4 thread mapping (NB = 1 only); WN_REP_TMA=0|1 period-block ring; WN_REP_SHARE=0: no shared bands.
+int rep_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsigned char *rows, int k0, int nx, int ny, int nk,
+             const WnBands &b, WnFold fold, float *out, cudaStream_t st)
+{
+    const int nb = b.nbands;
+    if (nb < 1 || nb > 2 || nx % 4 != 0 || (fold.P && fold.Lx % 4 != 0)) return 0;
+    if (ny > 8 * 65535 || nk > 32 * 65535) return 0;
+    int want_rx = 2, want_ry = 2, share = 1;
+    if (const char *e = getenv("WN_REP")) {
+        if (!strcmp(e, "0")) return 0;
+        if (strlen(e) == 2) { want_rx = e[0] - '0'; want_ry = e[1] - '0'; }
+    }
+    if (const char *e = getenv("WN_REP_SHARE")) share = atoi(e) != 0;
+    // which axes can be halved into replicas, and the first-tap-cell shift of every band between the halves
+    int cxs[2] = { 0, 0 }, cys[2] = { 0, 0 };
+    bool ok_x = want_rx == 2 && nx % 8 == 0 && (!fold.P || (nx / 2) % fold.Lx == 0);
+    bool ok_y = want_ry == 2 && ny % 2 == 0 && (!fold.P || (ny / 2) % fold.Ly == 0);
+    for (int i = 0; i < nb && ok_x; ++i) ok_x = axis_replica_shift(h.ex(rows[i]), h.fx(rows[i]), nx, &cxs[i]);
+    for (int i = 0; i < nb && ok_y; ++i) ok_y = axis_replica_shift(h.ey(rows[i]), h.fy(rows[i]), ny, &cys[i]);
+    const int ring_planes = nb == 1 ? 8 : 4;                   // RING of k_mb3d_rep
+    const size_t ring_bytes = fold.P ? (size_t)ring_planes * 256 * sizeof(float4) : 0;
+    // candidates in order of preference; the first one whose windows fit the registers and whose U rows leave room for
+    // two CTAs per SM (<= ~113 KB each) is used
+    const int cand[3][2] = { {2, 2}, {1, 2}, {1, 1} };
+    for (int ci = 0; ci < 3; ++ci) {
+        const int RX = cand[ci][0], RY = cand[ci][1], R = RX * RY;
+        if ((RX == 2 && !ok_x) || (RY == 2 && !ok_y)) continue;
+        WnRep rep{nx / RX, ny / RY, {cxs[0], cxs[1]}, {cys[0], cys[1]}, {0, 0, 0, 0}};
+        // trailing bands whose replicas coincide (shift = whole tile periods along every halved axis) are shared
+        int nsh = 0;
+        if (share && R > 1)
+            for (int i = nb - 1; i >= 1; --i) {
+                const bool same = (RX == 1 || cxs[i] % t.n == 0) && (RY == 1 || cys[i] % t.n == 0);
+                if (!same) break;
+                ++nsh;
+            }
+        const int windows = (nb - nsh) * R + nsh;
+        if (windows > (nsh ? 5 : 4)) continue;
+        int max_rows = 0;
+        bool ok = true;
+        for (int i = 0; i < nb && ok; ++i) {
+            const BrickPlan pb = plan_bricks(h, rows + i, 1, rep.by, k0, nk, 8, 32, 128, true);
+            ok = pb.ok;
+            max_rows += pb.max_rows * (i < nb - nsh ? R : 1);
+        }
+        if (!ok) return 0;                                     // unsorted axes / huge footprints: not a brick lattice
+        const size_t smem = ring_bytes + (size_t)max_rows * (128 * sizeof(float) + sizeof(int)) +
+                            (size_t)nb * (128 + 8 + 32) * sizeof(float4) + 64;
+        if (smem > 113 * 1024) continue;
+        int ypw = 1, tma = 1;
+        if (const char *e = getenv("WN_REP_YPW")) ypw = (atoi(e) == 4 && nb == 1) ? 4 : 1;
+        if (const char *e = getenv("WN_REP_TMA")) tma = atoi(e) != 0;
+        CUtensorMap pmap;
+        std::memset(&pmap, 0, sizeof(pmap));
+        tma = tma && fold.P && fold.Lx % 128 == 0 && fold.Ly % 8 == 0 && fold.Lz % 4 == 0 && fold.kphase % 4 == 0 &&
+              rep.bx % 128 == 0 && rep.by % 8 == 0 && nk % 32 == 0 &&
+              make_period_map(fold.P, fold.Lx, fold.Ly, fold.Lz, ring_planes / 2, &pmap);
+        for (int r = 0; r < 4; ++r)
+            rep.roff[r] = 4LL * ((long long)(r % RX) * rep.bx + (long long)nx * ((long long)(r / RX) * rep.by));
+#define WN_REP_CASE(NB_, NSH_, RX_, RY_, YPW_, TMA_)                                                                     \
+        if (nb == NB_ && nsh == NSH_ && RX == RX_ && RY == RY_ && ypw == YPW_ && tma == TMA_)                           \
+            return launch_rep<NB_, NSH_, RX_, RY_, YPW_, TMA_>(t, tabs, nx, ny, nk, out, max_rows, smem, fold, rep, pmap, st);
+#define WN_REP_CASES(NB_, NSH_, RX_, RY_) WN_REP_CASE(NB_, NSH_, RX_, RY_, 1, 1) WN_REP_CASE(NB_, NSH_, RX_, RY_, 1, 0)
+        WN_REP_CASES(1, 0, 1, 1) WN_REP_CASES(1, 0, 1, 2) WN_REP_CASES(1, 0, 2, 2)
+        WN_REP_CASE(1, 0, 1, 2, 4, 1) WN_REP_CASE(1, 0, 1, 2, 4, 0)
+        WN_REP_CASES(2, 0, 1, 1) WN_REP_CASES(2, 0, 1, 2)
+        WN_REP_CASES(2, 1, 1, 2) WN_REP_CASES(2, 1, 2, 2)
+#undef WN_REP_CASES
+#undef WN_REP_CASE
+    }
+    return 0;
+}
+
 // brick shapes (BY, BZ, threads); WN_BRICK=<index> overrides the default for tuning runs
 struct Shape { int by, bz, nt; };
 const Shape kShapes[] = { {16, 8, 256}, {16, 16, 256}, {8, 8, 256}, {8, 16, 256}, {8, 4, 256}, {16, 4, 256},
@@ -1030,6 +1566,10 @@ int brick_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsign
     // one or two bands left after folding: the z-streaming kernel (WN_COL4=0 disables it for A/B runs)
     const char *col4_env = getenv("WN_COL4");
     const bool col4_on = !col4_env || atoi(col4_env) != 0;
+    if (pick < 0 && can4 && col4_on && b.nbands >= 1 && b.nbands <= 2) {
+        const int r = rep_pass(t, tabs, h, rows, k0, nx, ny, nk, b, fold, out, st);
+        if (r != 0) return r;
+    }
     if (pick < 0 && can4 && col4_on && b.nbands >= 1 && b.nbands <= 2 && (ny + 7) / 8 <= 65535 && (nk + 31) / 32 <= 65535) {
         plan = plan_bricks(h, rows, b.nbands, ny, k0, nk, 8, 32, 128, true);
         if (plan.ok && plan.smem <= 56 * 1024) {
@@ -1238,7 +1778,7 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
         plan->host_axes = make_host_axes(h_xs, std::max(nx, 0), h_ys, std::max(ny, 0), h_zs, std::max(nz, 0), b, t.n);
         if (nx <= 0 || ny <= 0 || nz <= 0 || b.nbands <= 0) return 0;
         const size_t per_band = (size_t)nx + ny + nz;
-        if (cudaMallocAsync(&plan->tab, per_band * b.nbands * sizeof(float4), st) != cudaSuccess) return -1;
+        if (wn_scratch_alloc((void **)&plan->tab, per_band * b.nbands * sizeof(float4), st) != cudaSuccess) return -1;
         float4 *tx = plan->tab, *ty = tx + (size_t)b.nbands * nx, *tz = ty + (size_t)b.nbands * ny;
         const int total_e = (int)(per_band * b.nbands);
         launch_chained(plan->pdl != 0, k_axis_tables, dim3(std::min((total_e + 255) / 256, 1184)), dim3(256), 0, st, c, b, 0, nz, tx, ty, tz);
@@ -1273,7 +1813,7 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
         ++dst.nbands;
     }
     float *P = nullptr;
-    if (cudaMallocAsync(&P, (size_t)(Lx * Ly * Lz) * sizeof(float), st) != cudaSuccess) {
+    if (wn_scratch_alloc((void **)&P, (size_t)(Lx * Ly * Lz) * sizeof(float), st) != cudaSuccess) {
         cudaGetLastError();                                    // no scratch for the block: evaluate every band per sample
         return launched;
     }

@@ -213,8 +213,8 @@ int wn_launch_gaussian_fill(unsigned seed, float *out, size_t count, unsigned lo
     if (attempts >= 0xffffffffull) return -1;
     uint32_t *draws = nullptr, *bc = nullptr;
     const size_t nb = (attempts + PB - 1) / PB;
-    if (cudaMallocAsync(&draws, nblocks * MT_N * sizeof(uint32_t), st) != cudaSuccess) return -1;
-    if (cudaMallocAsync(&bc, nb * sizeof(uint32_t), st) != cudaSuccess) { cudaFreeAsync(draws, st); return -1; }
+    if (wn_scratch_alloc((void **)&draws, nblocks * MT_N * sizeof(uint32_t), st) != cudaSuccess) return -1;
+    if (wn_scratch_alloc((void **)&bc, nb * sizeof(uint32_t), st) != cudaSuccess) { cudaFreeAsync(draws, st); return -1; }
     k_mt19937<<<1, 512, 0, st>>>(seed, draws, (int)nblocks);
     k_polar_count<<<(unsigned)nb, PB, 0, st>>>(draws, attempts, bc);
     k_scan_blocks<<<1, 1024, 0, st>>>(bc, (int)nb, accepted);
