@@ -26,6 +26,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = "wavelet-noise-in-ray-tracing_b200"
 sys.path.insert(0, ROOT)
 
+# Host threads of the CPU reference arm: every core this process may run on, taken at import (before any NUMA binding)
+# and passed EXPLICITLY to the reference loop.  torchrun exports OMP_NUM_THREADS=1, so omp_get_max_threads() would
+# silently drop the reference to one thread at N >= 2 and make vs_reference mean something else at every N.
+HOST_THREADS = len(os.sched_getaffinity(0))
+
 VOLUME = 1024
 TILE_N = 128
 SEED = 12345
@@ -101,12 +106,24 @@ class ClockSampler:
         return out
 
 
+TRAFFIC_CSV = "profiles/r2_main_raw.csv"
+
+
+def extra_peaks():
+    """Roofline denominators MEASURED_PEAKS.json does not hold (FP32 FMA rate, L2 read bandwidth, HBM write stream,
+    pinned D2H): measured once on this pool's B200 by profiles/scripts/peaks.cu, committed as profiles/r2_peaks.json."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_peaks.json")))
+    except (OSError, ValueError):
+        return {}
+
+
 def profiled_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (the longest launch in the capture), one
-    launch at N=1 bench size, from the committed `ncu --set full` capture (profiles/r1_col4_raw.csv); None when the
-    capture is missing."""
+    launch at N=1 bench size, from the committed `ncu --set full` capture (TRAFFIC_CSV); None when the capture is
+    missing."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_col4_raw.csv")
+    path = os.path.join(ROOT, TRAFFIC_CSV)
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
@@ -140,13 +157,13 @@ def cpu_reference_rate(ax, scale, w, post, target_seconds, threads=0):
     if RefLib.available():
         ref = RefLib()
         noise = ref.noise(TILE_N, SEED).generate(3)
-        cores = ref.max_threads() if threads <= 0 else threads
+        cores = HOST_THREADS if threads <= 0 else threads
         run = lambda zs: noise.multiband3d_lattice(ax, ax, zs, scale, w, post, threads=cores)   # noqa: E731
         kind = "reference"
     else:
         orc = Oracle()
         tile = orc.generate_tile(TILE_N, SEED, 3)
-        cores = orc.max_threads() if threads <= 0 else threads
+        cores = HOST_THREADS if threads <= 0 else threads
         run = lambda zs: orc.multiband3d_lattice(tile, TILE_N, ax, ax, zs, scale, w, post, threads=cores)   # noqa: E731
         kind = "port"
     t0 = time.perf_counter()
@@ -276,6 +293,45 @@ def run_ours(args, rank, world, local_rank):
     total_samples = VOLUME ** 3 * args.steps
     value = total_samples / (elapsed_ms * 1e-3) / 1e9
 
+    # --- dominant kernel alone, measured live: the same steps again with one CUDA-event pair around the main kernel of
+    # every call (recorded by the library on the stream the kernel is launched on).  Kept out of the timed region above
+    # because an event between the period-block chain and the main kernel removes their dependent-launch overlap.
+    ctx.time_main_kernel(True)
+    for _ in range(args.steps):
+        step()
+    main_ms = ctx.main_kernel_ms()
+    ctx.time_main_kernel(False)
+    main_kernel_ms = float(np.mean(main_ms)) if main_ms.size else None
+
+    # --- the general path: the same five bands on a lattice that is NOT commensurate with the tile (base range 4.1
+    # instead of 4: no band repeats, nothing folds, no replicas), i.e. the honest per-sample WMultibandNoise cost
+    unfolded = None
+    if rank == 0 and world == 1:
+        axu = (np.arange(VOLUME, dtype=np.float32) / np.float32(VOLUME)) * np.float32(4.1)
+        nzu = 256
+        outu = out[:nzu]
+        for _ in range(2):
+            noise.multiband3D_lattice(axu, axu, axu[:nzu], scale, w, float(post), mode=wn.WN_EVAL_FAST, out=outu)
+        torch.cuda.synchronize()
+        ua, ub = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ua.record()
+        for _ in range(3):
+            noise.multiband3D_lattice(axu, axu, axu[:nzu], scale, w, float(post), mode=wn.WN_EVAL_FAST, out=outu)
+        ub.record()
+        torch.cuda.synchronize()
+        u_ms = ua.elapsed_time(ub) / 3
+        u_rate = VOLUME * VOLUME * nzu / (u_ms * 1e-3) / 1e9
+        xp = extra_peaks()
+        fp32_peak = xp.get("fp32_fma_tflops")
+        u_tflops = u_rate * 1e9 * FLOP_PER_SAMPLE / 1e12
+        unfolded = {"workload": f"same bands, lattice {VOLUME}x{VOLUME}x{nzu} with base range 4.1 (not commensurate with "
+                                "the tile: every band evaluated per sample)",
+                    "value": u_rate, "unit": UNIT, "ms_per_call": u_ms,
+                    "roofline": {"bound": "fp32", "flop_per_sample": FLOP_PER_SAMPLE, "achieved": u_tflops,
+                                 "peak": fp32_peak, "unit": "TFLOP/s",
+                                 "frac": (u_tflops / fp32_peak) if fp32_peak else None,
+                                 "peak_source": "profiles/r2_peaks.json fp32_fma_tflops (dependent FFMA chains, measured)"}}
+
     # --- e2e: the public host-buffer call (axes H2D, result D2H into pinned host memory inside the timed region)
     e2e_steps = min(args.steps, 5)
     host_out = torch.empty((nz_local, VOLUME, VOLUME), dtype=torch.float32, pin_memory=True)
@@ -296,25 +352,33 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = VOLUME ** 3 * e2e_steps / float(t.item()) / 1e9
     h2d_bytes = int((ax.nbytes * 2 + zs.nbytes) + scale.nbytes + w.nbytes)
     d2h_bytes = int(samples_local * 4)
-    # sanity: the e2e result equals the device-resident result
-    same = bool(torch.equal(host_out[:1], out[:1].cpu()))
+    # sanity: the e2e result equals the device-resident result (one slice of every 32-slice staging chunk)
+    same = all(bool(torch.equal(host_out[k], out[k].cpu())) for k in range(0, nz_local, 32))
     del host_out
 
     if rank != 0:
         return
     hbm_peak, peak_src = peaks()
-    med_launch_ms = float(np.median(per_launch_ms))
-    achieved_gbs = samples_local * OUT_BYTES_PER_SAMPLE / (med_launch_ms * 1e-3) / 1e9
+    xp = extra_peaks()
+    med_step_ms = float(np.median(per_launch_ms))
+    alg_bytes = samples_local * OUT_BYTES_PER_SAMPLE + TILE_N ** 3 * 4
+    kern_ms = main_kernel_ms if main_kernel_ms else med_step_ms
+    achieved_gbs = alg_bytes / (kern_ms * 1e-3) / 1e9
+    step_gbs = alg_bytes / (med_step_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "k_mb3d_col4 (multiband lattice; timed over all launches of one step)",
+        "bound": "hbm", "kernel": "k_mb3d_rep (main kernel of the multiband lattice call: the launch that writes the output)",
         "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
         "peak_source": peak_src,
         "traffic": profiled_traffic_bytes() if world == 1 else None,
-        "traffic_source": "profiles/r1_col4_raw.csv (ncu --set full, main-kernel launch at N=1 bench size)",
-        "algorithmic_bytes_per_launch": samples_local * OUT_BYTES_PER_SAMPLE + TILE_N ** 3 * 4,
-        "launch_ms": med_launch_ms,
+        "traffic_source": TRAFFIC_CSV + " (ncu --set full, main-kernel launch at N=1 bench size)",
+        "algorithmic_bytes_per_launch": alg_bytes,
+        "launch_ms": kern_ms,
+        "launch_ms_source": "mean over the steps of the CUDA-event pair the library records around the main kernel",
+        "step": {"achieved": step_gbs, "frac": step_gbs / hbm_peak, "ms": med_step_ms,
+                 "note": "all launches of one step (axis tables, period blocks, main kernel), median over the timed steps"},
+        "hbm_write_stream_gbs": xp.get("hbm_write_gbs"),
         "fp32": {"flop_per_sample": FLOP_PER_SAMPLE,
-                 "achieved_tflops": samples_local * FLOP_PER_SAMPLE / (med_launch_ms * 1e-3) / 1e12,
+                 "achieved_tflops": samples_local * FLOP_PER_SAMPLE / (med_step_ms * 1e-3) / 1e12,
                  "note": "SURVEY 8(d) algorithmic FLOP (5 bands x 95) per sample; four of the five bands are periodic on this lattice and are evaluated once per period, so the main kernel is bound by the 4 B/sample output stream"},
     }
     # tile-gen ms at n=128 (second half of BASELINE's metric)
@@ -364,7 +428,11 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": f"z block-cyclic x{world}, no data-path collective",
                    "l2": "each step writes 4 GiB/N of fresh output (>> 126 MB L2); the 8 MiB tile is L2-resident by design"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "steps": e2e_steps, "matches_device_result": same, "numa_bound": prev_affinity is not None},
+                "steps": e2e_steps, "matches_device_result": same, "numa_bound": prev_affinity is not None,
+                "ceiling": {"d2h_pinned_gbs_one_gpu": xp.get("d2h_pinned_gbs"),
+                            "value": (xp["d2h_pinned_gbs"] / 4.0 * min(world, 1)) if xp.get("d2h_pinned_gbs") else None,
+                            "note": "4 bytes per sample cross PCIe: pinned D2H bandwidth / 4 (one GPU; profiles/r2_peaks.json)"}},
+        "unfolded": unfolded,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -76,6 +76,12 @@ const char *wn_version(void);
 uint64_t    wn_kernel_launches(const wn_ctx *ctx);
 /* CUDA-event time of the kernels enqueued by the most recent WN_HOST call on this context (ms) */
 float       wn_timing_last_ms(const wn_ctx *ctx);
+/* Per-call CUDA-event timing of the MAIN kernel (the launch that writes the output) of WN_DEVICE, WN_EVAL_FAST
+ * wn_multiband3d_lattice calls, for roofline reports: enable, run calls, then collect (synchronises the stream; ms[i] =
+ * duration of call i's main kernel; *count = calls recorded, which may exceed capacity).  The events sit between the
+ * period-block chain and the main kernel, so dependent-launch overlap across that boundary is lost while enabled. */
+int         wn_timing_main_kernel_enable(wn_ctx *ctx, int on);
+int         wn_timing_main_kernel_collect(wn_ctx *ctx, float *ms, int capacity, int *count);
 /* Host-only (no GPU needed): which bands a WN_EVAL_FAST wn_multiband3d_lattice call on these axes would evaluate once
  * per period ("fold") at its top level for a tile of edge tile_n.  band_folded[nbands] receives 0/1 in the caller's
  * band order, block[3] the period block Lx, Ly, Lz in samples (1,1,1 when nothing folds); *nfolded the count.  The
@@ -83,6 +89,13 @@ float       wn_timing_last_ms(const wn_ctx *ctx);
 int         wn_debug_fold_plan(const float *xs, int nx, const float *ys, int ny, const float *zs, int nz,
                                const float *band_scale, int nbands, int tile_n,
                                int *band_folded, int block[3], int *nfolded);
+
+/* Diagnostics (GPU): the axis-table entries the FAST lattice kernels use for `count` coordinates of one axis at one
+ * band scale, computed by the same kernel as in a real call: weights3[3i..3i+2] = the three quadratic B-spline weights
+ * (WaveletNoise.cpp:194-200, un-fused), first_cell[i] = mid - 1 (the first of the three tap cells, NOT wrapped; the taps
+ * are Mod(first_cell + f, n), f = 0..2 -- the reference's indices cpp:202-209).  Host pointers. */
+int         wn_debug_axis_entries(wn_ctx *ctx, const float *coords, int count, float band_scale,
+                                  float *weights3, int32_t *first_cell);
 
 /* ---- context ------------------------------------------------------------------------------ */
 int  wn_ctx_create(int device /* -1 = current */, wn_ctx **out);

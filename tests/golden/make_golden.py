@@ -88,6 +88,34 @@ def main():
     out["tex_wavelet2d_s0.37_o3"] = ref.texture_values("wavelet2d", 0.37, 3, tp)
     out["tex_perlin_s1_o4"] = ref.texture_values("perlin", 1.0, 4, tp)
     out["tex_perlin_s0.37_o5"] = ref.texture_values("perlin", 0.37, 5, tp)
+    # projected noise far from the origin and with normals on / next to a coordinate axis (the row culling of k_proj
+    # must only ever skip candidates the reference weighs with 0): |p| ~ 1e3 .. 1e6, 16 normals per magnitude class
+    hp, hn = [], []
+    axes = np.eye(3)
+    for mag in (1.0e3, 1.0e4, 1.0e5, 1.0e6):
+        for k in range(64):
+            p = rs.uniform(-1, 1, 3) * mag
+            if k % 4 == 0:
+                p = np.round(p)                                  # integer coordinates
+            elif k % 4 == 1:
+                p = np.round(p * 2) / 2                          # half-integers
+            a = axes[k % 3] * (1 if (k // 3) % 2 == 0 else -1)
+            kind = (k // 6) % 4
+            if kind == 0:
+                nv = a                                           # exactly on an axis
+            elif kind == 1:
+                nv = a + rs.normal(size=3) * 1e-4                # within 1e-4 of an axis
+            elif kind == 2:
+                nv = a + rs.normal(size=3) * 1e-6
+            else:
+                nv = rs.normal(size=3)                           # generic
+            nv = nv / np.linalg.norm(nv)
+            hp.append(p)
+            hn.append(nv)
+    hp, hn = np.array(hp, np.float32), np.array(hn, np.float32)
+    out["proj_huge_pts"], out["proj_huge_normals"] = hp, hn
+    out["proj_huge"] = n3.eval3d_projected_points(hp, hn)
+    out["proj_huge_n30"] = t30.eval3d_projected_points(hp, hn)
     np.savez_compressed(os.path.join(HERE, "ref_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

@@ -86,24 +86,30 @@ def test_fold_plan_host_logic(monkeypatch):
         monkeypatch.delenv(k, raising=False)
     ax = sh.lattice_axes_config3(1024)
     scale, _, _ = sh.config3_bands(4, 8)
-    # whole volume: bands 5..8 repeat (periods 512/256/128/64 samples), band 4's period is the lattice itself
+    # whole volume: bands 5..8 repeat (periods 512/256/128/64 samples), band 4's period is the lattice itself.  Bands 6..8
+    # fold onto a 256^3 block; band 5 stays direct because the replica kernel evaluates it once per four samples (the x
+    # and y halves of the lattice are a whole number of its periods apart) and a 512^3 block would cost an HBM round trip
     folded, block = wn.fold_plan(ax, ax, ax, scale, 128)
-    assert list(folded) == [False, True, True, True, True] and block == (512, 512, 512)
+    assert list(folded) == [False, False, True, True, True] and block == (256, 256, 256)
     # the decision follows the bands, not their order in the call
     perm = [3, 0, 4, 2, 1]
     folded_p, block_p = wn.fold_plan(ax, ax, ax, scale[perm], 128)
-    assert list(folded_p) == [True, False, True, True, True] and block_p == block
-    # contiguous 128-slice slab (1/8 of the volume): no whole z period of band 5 -> the block spans the slab in z
+    assert list(folded_p) == [True, False, True, True, False] and block_p == block
+    # contiguous 128-slice slab (1/8 of the volume): no whole z period of band 6 -> the block spans the slab in z
     folded, block = wn.fold_plan(ax, ax, ax[:128], scale, 128)
-    assert list(folded) == [False, True, True, True, True] and block == (512, 512, 128)
-    # block-cyclic shard of rank 3 of 8: slices congruent modulo 256 stay together -> z period 64 for band 5
+    assert list(folded) == [False, False, True, True, True] and block == (256, 256, 128)
+    # block-cyclic shard of rank 3 of 8: slices congruent modulo 256 stay together -> z period 32 for band 6
     zs = ax[sh.cyclic_slab_indices(1024, 3, 8)]
     folded, block = wn.fold_plan(ax, ax, zs, scale, 128)
-    assert list(folded) == [False, True, True, True, True] and block == (512, 512, 64)
-    # a smaller budget (64 MiB = 2^24 samples) keeps band 5 per sample
-    monkeypatch.setenv("WN_FOLD_BUDGET", str(1 << 24))
+    assert list(folded) == [False, False, True, True, True] and block == (256, 256, 32)
+    # x extent 1536: the halves are 1.5 periods of band 5 apart, so its replicas do not coincide -> band 5 folds too
+    ax15 = (np.arange(1536, dtype=np.float32) / np.float32(1024)) * np.float32(4.0)
+    folded, block = wn.fold_plan(ax15, ax, ax, scale, 128)
+    assert list(folded) == [False, True, True, True, True] and block == (512, 512, 512)
+    # a smaller budget (2^21 samples) keeps band 6 per sample as well
+    monkeypatch.setenv("WN_FOLD_BUDGET", str(1 << 21))
     folded, block = wn.fold_plan(ax, ax, ax, scale, 128)
-    assert list(folded) == [False, False, True, True, True] and block == (256, 256, 256)
+    assert list(folded) == [False, False, False, True, True] and block == (128, 128, 128)
     monkeypatch.setenv("WN_FOLD_BUDGET", "0")
     assert not wn.fold_plan(ax, ax, ax, scale, 128)[0].any()
     monkeypatch.delenv("WN_FOLD_BUDGET")

@@ -161,6 +161,31 @@ def test_points_match_reference_vectors(wn, gpu_tiles, ref_vectors):
         assert_bits(wn.PerlinNoise(seed).noise_points(pts[:5376]), rv[f"perlin_{seed}"], f"perlin {seed}")
 
 
+def test_projected_far_from_origin_and_axis_normals(wn, oracle, gpu_tiles, tiles128, ref_vectors):
+    """k_proj skips rows of the candidate box that cannot contribute; the skip must never drop a tap the reference
+    weighs above its 1e-6 threshold.  |p| ~ 1e3 .. 1e6 (float spacing up to 1/16), normals exactly on an axis, within
+    1e-4 / 1e-6 of one, and generic: bit-exact against vectors generated by the unmodified reference, for per-point
+    normals, for each normal shared by a batch, and on the non-power-of-two tile."""
+    rv = ref_vectors
+    hp, hn = rv["proj_huge_pts"], rv["proj_huge_normals"]
+    assert_bits(gpu_tiles[3].evaluate3DProjected_points(hp, hn), rv["proj_huge"], "projected, huge |p|")
+    for k in range(0, hp.shape[0], 7):                       # shared-normal entry point, one normal at a time
+        got = gpu_tiles[3].evaluate3DProjected_points(hp[k:k + 1], hn[k])
+        assert_bits(got, rv["proj_huge"][k:k + 1], f"projected shared normal {k}")
+    w = wn.WaveletNoise(30, 807)
+    w.generateNoiseTile3D()
+    assert_bits(w.evaluate3DProjected_points(hp, hn), rv["proj_huge_n30"], "projected n=30, huge |p|")
+    # more of the same against the oracle (pinned on the vectors above by tests/test_oracle_cpu.py)
+    rs = np.random.RandomState(77)
+    for mag in (1e3, 1e4, 1e5, 1e6):
+        p = (rs.uniform(-1, 1, (4096, 3)) * mag).astype(np.float32)
+        nv = np.eye(3)[rs.randint(0, 3, 4096)] * rs.choice([-1.0, 1.0], (4096, 1)) + rs.normal(size=(4096, 3)) * \
+            rs.choice([0.0, 1e-6, 1e-4, 1e-2], (4096, 1))
+        nv = (nv / np.linalg.norm(nv, axis=1, keepdims=True)).astype(np.float32)
+        want = oracle.eval3d_projected_points(tiles128[3], 128, p, nv)
+        assert_bits(gpu_tiles[3].evaluate3DProjected_points(p, nv), want, f"projected |p|~{mag:g}")
+
+
 def test_non_pow2_tile_evaluation(wn, oracle, ref_vectors):
     rv = ref_vectors
     w = wn.WaveletNoise(30, 807)
@@ -223,7 +248,7 @@ def lattice_axis(idx, size=1024):
 def test_multiband_lattice_subvolumes(wn, oracle, gpu_tiles, tiles128, mode):
     rs = np.random.RandomState(3)
     rng = float(tiles128[3].max() - tiles128[3].min())
-    tol = 1e-5 * rng * float(WEIGHTS.sum()) * float(POST)
+    tol = 1e-5 * rng                    # strict north_star bound (measured 1.4e-6), not inflated by sum(w) * post
     for trial in range(6):
         x0, y0, z0 = rs.randint(0, 1024 - 40, 3)
         nx, ny, nz = (40, 33, 9) if trial % 2 else (37, 16, 12)
@@ -296,6 +321,92 @@ def test_projected_and_perlin_affine_grid_config4(wn, oracle, gpu_tiles, tiles12
     gp = pn.noise_grid(origin, e1, us, e2, vs, float(f(2.0 ** 4)))
     P4 = ((origin[None, None, :] + U[..., None] * e1) + V[..., None] * e2).astype(f) * f(2.0 ** 4)
     assert_bits(gp, oracle.perlin_points(oracle.perlin_perm(12345), P4.reshape(-1, 3)).reshape(80, 96), "perlin affine grid")
+
+
+def test_config4_full_size_8192_squared(wn, oracle, gpu_tiles, tiles128):
+    """BASELINE config 4 at its full size: WProjectedNoise on the 8192^2 oblique plane and Perlin(12345) octave 4 on the
+    same grid, device resident.  65 536 random pixels plus two full rows (first / last) and two full columns against
+    the oracle, BIT-EXACT (the affine coordinate formula is evaluated un-fused in a fixed order on both sides)."""
+    import torch
+    f = np.float32
+    S = 8192
+    nrm = (np.array([1, 2, 3], np.float64) / np.sqrt(14.0)).astype(f)
+    e1 = (np.array([2, -1, 0], np.float64) / np.sqrt(5.0)).astype(f)
+    e2 = (np.array([3, 6, -5], np.float64) / np.sqrt(70.0)).astype(f)
+    origin = np.array([0, 0, 1], f)
+    ax = (np.arange(S, dtype=f) / f(S)) * f(4)
+    pre_w, pre_p = f(2.0 * 2 ** 4), f(2.0 ** 4)
+    inv = f(1.0) / np.sqrt(f(0.296))
+    t = gpu_tiles[3]
+    proj = t.evaluate3DProjected_grid(origin, e1, ax, e2, ax, nrm, float(pre_w), float(inv), device_out=True)
+    perlin = wn.PerlinNoise(12345, t.ctx)
+    perl = perlin.noise_grid(origin, e1, ax, e2, ax, float(pre_p), device_out=True)
+    t.ctx.synchronize()
+    proj, perl = proj.cpu().numpy(), perl.cpu().numpy()
+    assert proj.shape == (S, S) and np.isfinite(proj).all() and np.isfinite(perl).all()
+    rs = np.random.RandomState(4)
+    ii = np.concatenate([rs.randint(0, S, 1 << 16), np.arange(S), np.arange(S), np.zeros(S, int), np.full(S, S - 1)])
+    jj = np.concatenate([rs.randint(0, S, 1 << 16), np.zeros(S, int), np.full(S, S - 1), np.arange(S), np.arange(S)])
+    P = ((origin[None, :] + ax[ii][:, None] * e1) + ax[jj][:, None] * e2).astype(f)
+    want = oracle.eval3d_projected_points(tiles128[3], 128, P * pre_w, nrm, 1.0, inv)
+    assert_bits(proj[jj, ii], want, "config 4 projected, 8192^2")
+    wantp = oracle.perlin_points(oracle.perlin_perm(12345), P * pre_p)
+    assert_bits(perl[jj, ii], wantp, "config 4 Perlin, 8192^2")
+    # FP32 fast mode of the Perlin kernel: opt-in, within 1e-5 * range (range of Perlin noise = 2) of the FP64 kernel
+    perlin.set_precision(wn.WN_PERLIN_F32)
+    fast = perlin.noise_grid(origin, e1, ax, e2, ax, float(pre_p), device_out=True)
+    t.ctx.synchronize()
+    assert float(np.abs(fast.cpu().numpy() - perl).max()) <= 1e-5 * 2.0
+    perlin.set_precision(wn.WN_PERLIN_F64)
+    again = perlin.noise_grid(origin, e1, ax[:64], e2, ax[:64], float(pre_p))
+    assert_bits(again, perl[:64, :64], "back to FP64")
+
+
+def test_perlin_double_precision_entry(wn, oracle):
+    """PerlinNoise::noise(double, double, double): coordinates that are NOT float-valued, double result (no narrowing)."""
+    pn = wn.PerlinNoise(12345)
+    perm = oracle.perlin_perm(12345)
+    rs = np.random.RandomState(8)
+    pts = rs.uniform(-300, 300, (512, 3))
+    got = pn.noise_points_f64(pts)
+    want = np.array([oracle.perlin_noise(perm, *p) for p in pts])
+    assert (got.view(np.uint64) == want.view(np.uint64)).all()
+    assert pn.noise(0.1, 0.2, 0.3) == oracle.perlin_noise(perm, 0.1, 0.2, 0.3)
+    assert pn.noise(0.3, 0.7) == oracle.perlin_noise(perm, 0.3, 0.7, 0.0)
+
+
+def test_axis_table_tap_cells_are_the_reference_integers(wn, oracle, gpu_tiles):
+    """north_star: "bit-exact tile indexing".  The tap cells of the FAST lattice kernels (k_axis_tables: first cell +
+    0..2, wrapped) are compared AS INTEGERS with the 27 tile indices the reference's evaluate3D gathers
+    (orc_eval3d_taps restates cpp:194-209), for coordinates that are negative, huge, on cell and half-cell boundaries,
+    and for a power-of-two and a non-power-of-two tile edge; the weights must equal the un-fused reference formula."""
+    ctx = gpu_tiles[3].ctx
+    rs = np.random.RandomState(21)
+    coords = np.concatenate([rs.uniform(-300, 300, 2048), rs.uniform(-2, 2, 512), np.round(rs.uniform(-64, 64, 512) * 2) / 2,
+                             rs.uniform(-1, 1, 256) * 1e6, [0.0, 0.5, -0.5, 127.5, 128.0, -128.0, 2.0, 2.5]]).astype(np.float32)
+    coords = coords[: coords.size // 3 * 3]
+    for scale in (1.0, 32.0, 0.37):
+        w, first = ctx.axis_entries(coords, scale)
+        q = coords * np.float32(scale)
+        # reference weights, un-fused float32 (cpp:194-200)
+        a = q - np.float32(0.5)
+        mid = np.ceil(a)
+        t = (mid - a).astype(np.float32)
+        w0 = (t * t * np.float32(0.5)).astype(np.float32)
+        s1 = (np.float32(1.0) - t).astype(np.float32)
+        w2 = (s1 * s1 * np.float32(0.5)).astype(np.float32)
+        w1 = ((np.float32(1.0) - w0).astype(np.float32) - w2).astype(np.float32)
+        assert_bits(w[:, 0], w0, "w0"); assert_bits(w[:, 1], w1, "w1"); assert_bits(w[:, 2], w2, "w2")
+        for n in (128, 30):
+            pts = q.reshape(-1, 3)
+            f3 = first.reshape(-1, 3)
+            for p, f in zip(pts[::7], f3[::7]):
+                idx = oracle.eval3d_taps(n, p)                     # 27 linear indices, fz outer, fx inner
+                cx = [(int(f[0]) + k) % n for k in range(3)]
+                cy = [(int(f[1]) + k) % n for k in range(3)]
+                cz = [(int(f[2]) + k) % n for k in range(3)]
+                mine = [cx[fx] + n * cy[fy] + n * n * cz[fz] for fz in range(3) for fy in range(3) for fx in range(3)]
+                assert list(idx) == mine, (p, n)
 
 
 def test_large_host_call_is_chunked_consistently(wn, gpu_tiles):
@@ -391,6 +502,42 @@ def test_fast_result_does_not_depend_on_folding_or_kernel(wn, gpu_tiles, monkeyp
     assert_bits(got, base, "band order")
 
 
+def test_replica_kernel_variants_are_bit_identical(wn, oracle, gpu_tiles, tiles128, monkeypatch):
+    """k_mb3d_rep (period-block value shared between x / y replicas, shared bands, TMA or cp.async ring) against the
+    round-1 z-streaming kernel (WN_REP=0) and the exact kernel: every variant must produce the SAME bits, on whole
+    bricks (TMA eligible), partial bricks, lattices whose halves are not replicas, and a z axis that jumps by more than
+    three cells inside a brick (the advance-mask fallback)."""
+    t = gpu_tiles[3]
+    ax = lattice_axis(np.arange(1024))
+    rng = float(tiles128[3].max() - tiles128[3].min())
+    zjump = np.concatenate([ax[:20], ax[400:420], ax[900:924]])          # 64 slices, jumps of 47.5 and 60 cells at band 4
+    cases = [
+        (ax, ax[:512], ax[:64], BANDS, WEIGHTS),            # x and y replicas, shared band 5, whole bricks
+        (ax[:512], ax[:512], ax[:96], BANDS[1:], WEIGHTS[1:]),   # replicas at stride 256
+        (ax[:1000], ax[:500], ax[:40], BANDS, WEIGHTS),     # halves are not replicas; partial bricks
+        (ax[:520], ax[:260], ax[:33], BANDS[:2], WEIGHTS[:2]),   # no fold at all (two direct bands), partial bricks
+        (ax[:256], ax[:64], zjump, BANDS[:1], WEIGHTS[:1]),      # jumps inside a brick: advance-mask fallback
+        (ax[:512], ax[:256], zjump, BANDS, WEIGHTS),
+    ]
+    variants = [{"WN_REP": "0"}, {}, {"WN_REP_TMA": "0"}, {"WN_REP": "12"}, {"WN_REP": "11"}, {"WN_REP_SHARE": "0"},
+                {"WN_REP": "12", "WN_REP_YPW": "4"}, {"WN_FOLD_BUDGET": str(1 << 27), "WN_REP_TMA": "1"},
+                {"WN_FOLD_BUDGET": str(1 << 27), "WN_REP": "22", "WN_REP_TMA": "0"}]
+    for ci, (xs, ys, zs, bs, ws) in enumerate(cases):
+        base = None
+        for env in variants:
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            got = t.multiband3D_lattice(xs, ys, zs, bs, ws, float(POST))
+            for k in env:
+                monkeypatch.delenv(k)
+            if base is None:
+                base = got
+                exact = t.multiband3D_lattice(xs, ys, zs[:8], bs, ws, float(POST), mode=wn.WN_EVAL_EXACT)
+                assert np.abs(got[:8] - exact).max() <= 1e-5 * rng, ci
+            else:
+                assert_bits(got, base, f"case {ci} {env}")
+
+
 def test_back_to_back_device_calls_with_tile_rebuilds(wn, monkeypatch):
     """Consecutive device-resident FAST calls without any synchronisation in between (the period-block chain of call
     i+1 runs on the side stream while call i's main kernel is still in flight), with different lattices and the tile
@@ -438,37 +585,71 @@ def test_argument_errors(wn, gpu_tiles):
 
 
 def test_config3_full_size_1024_cubed(wn, oracle, gpu_tiles, tiles128):
-    """BASELINE config 3 at its full size (1024^3 samples, 4 GiB, device resident): size-independent properties.
-    (1) linearity: the 5-band result equals the weighted sum of five single-band evaluations;
-    (2) statistics: finite everywhere, mean ~ 0, variance of order 1 (0.53 measured: bands 7 and 8 are sampled at
-        >= 1 cell per sample, where the band variance is below the continuous-sampling constant 0.18402);
-    (3) 4096 random samples against the CPU oracle within the FAST tolerance."""
+    """BASELINE config 3 at its full size (1024^3 samples, 4 GiB, device resident).
+    (1) EXACT (reference operation order) vs the CPU oracle, BIT-EXACT, on: 64 random 32^3 bricks; the full planes on
+        both sides of every period-block wrap (z = 127/128, 255/256, 511/512), of the 32-slice CTA brick edges next to
+        them (z = 31/32, 479/480, 991/992) and the last plane (1023); the x = 511/512 and y = 511/512 planes' rows where
+        the in-thread replicas of the main kernel meet.
+    (2) FAST vs EXACT over the WHOLE volume on the device: max |diff| <= 1e-5 * (tile max - tile min) -- the strict
+        north_star bound, NOT inflated by the band weights or the post scale.  With (1) this bounds FAST against the
+        reference everywhere, including every seam of the fold / replica / brick machinery.
+    (3) linearity: the 5-band result equals the weighted sum of five single-band evaluations; finite, mean ~ 0,
+        variance of order 1."""
     import torch
     t = gpu_tiles[3]
     t.ctx.use_torch_stream()
     try:
         ax = lattice_axis(np.arange(1024))
+        rng = float(tiles128[3].max() - tiles128[3].min())
+        strict = 1e-5 * rng
         full = t.multiband3D_lattice(ax, ax, ax, BANDS, WEIGHTS, float(POST), device_out=True)
+        # (2) whole volume, 64 slices at a time
+        exact = torch.empty((64, 1024, 1024), dtype=torch.float32, device=full.device)
+        worst = 0.0
+        seam_planes = [31, 32, 127, 128, 255, 256, 479, 480, 511, 512, 991, 992, 1023]
+        kept = {}
+        for z0 in range(0, 1024, 64):
+            t.multiband3D_lattice(ax, ax, ax[z0:z0 + 64], BANDS, WEIGHTS, float(POST), mode=wn.WN_EVAL_EXACT, out=exact)
+            worst = max(worst, float((full[z0:z0 + 64] - exact).abs().max()))
+            for z in seam_planes:
+                if z0 <= z < z0 + 64:
+                    kept[z] = exact[z - z0].cpu().numpy()
+        assert worst <= strict, (worst, strict)
+        # (1) exact vs oracle, bit for bit
+        for z, plane in kept.items():
+            want = oracle.multiband3d_lattice(tiles128[3], 128, ax, ax, ax[z:z + 1], BANDS, WEIGHTS, POST)[0]
+            assert_bits(plane, want, f"exact plane z={z}")
+        rs = np.random.RandomState(9)
+        for trial in range(64):
+            x0, y0, z0 = (int(v) for v in rs.randint(0, 1024 - 32, 3))
+            if trial < 8:                                          # bricks straddling the replica seams x / y = 512
+                x0, y0 = (496, y0) if trial % 2 else (x0, 496)
+            got = t.multiband3D_lattice(ax[x0:x0 + 32], ax[y0:y0 + 32], ax[z0:z0 + 32], BANDS, WEIGHTS, float(POST),
+                                        mode=wn.WN_EVAL_EXACT)
+            want = oracle.multiband3d_lattice(tiles128[3], 128, ax[x0:x0 + 32], ax[y0:y0 + 32], ax[z0:z0 + 32], BANDS,
+                                              WEIGHTS, POST)
+            assert_bits(got, want, f"exact brick {x0},{y0},{z0}")
+            sub = full[z0:z0 + 32, y0:y0 + 32, x0:x0 + 32].cpu().numpy()
+            assert np.abs(sub - want).max() <= strict
+        # the x = 511/512 and y = 511/512 seams of the FAST volume against the oracle on a few planes
+        for z in (0, 300, 777):
+            want = oracle.multiband3d_lattice(tiles128[3], 128, ax[504:520], ax, ax[z:z + 1], BANDS, WEIGHTS, POST)[0]
+            assert np.abs(full[z, :, 504:520].cpu().numpy() - want).max() <= strict
+            want = oracle.multiband3d_lattice(tiles128[3], 128, ax, ax[504:520], ax[z:z + 1], BANDS, WEIGHTS, POST)[0]
+            assert np.abs(full[z, 504:520, :].cpu().numpy() - want).max() <= strict
+        del exact
+        # (3)
         acc = torch.zeros_like(full)
         tmp = torch.empty_like(full)
         for b in range(len(BANDS)):
             t.multiband3D_lattice(ax, ax, ax, BANDS[b:b + 1], WEIGHTS[b:b + 1], float(POST), out=tmp)
             acc += tmp
         torch.cuda.synchronize()
-        rng = float(tiles128[3].max() - tiles128[3].min())
-        tol = 1e-5 * rng * float(WEIGHTS.sum()) * float(POST)
-        assert float((full - acc).abs().max()) <= tol
+        assert float((full - acc).abs().max()) <= strict
         del acc, tmp
         assert bool(torch.isfinite(full).all())
         mean = float(full.double().mean())
         var = float(full.double().var())
         assert abs(mean) < 0.01 and 0.4 < var < 0.7, (mean, var)
-        rs = np.random.RandomState(9)
-        idx = rs.randint(0, 1024, (4096, 3))
-        got = full[torch.from_numpy(idx[:, 2]).cuda(), torch.from_numpy(idx[:, 1]).cuda(),
-                   torch.from_numpy(idx[:, 0]).cuda()].cpu().numpy()
-        pts = np.stack([ax[idx[:, 0]], ax[idx[:, 1]], ax[idx[:, 2]]], -1)
-        want = oracle.multiband3d_points(tiles128[3], 128, pts, BANDS, WEIGHTS, POST)
-        assert np.abs(got - want).max() <= tol
     finally:
         t.ctx.set_stream(None)

@@ -28,7 +28,9 @@ from . import _lib
 from ._lib import (WN_DEVICE, WN_EVAL_EXACT, WN_EVAL_FAST, WN_HOST, WN_TILE_DEFAULT, WN_TILE_ODD_OFFSET, WnError,
                    WnStats, check, lib)
 
-__all__ = ["Context", "WaveletNoise", "PerlinNoise", "wavelet_texture", "noise_texture", "DataStats", "WnError",
+from ._lib import WN_PERLIN_F32, WN_PERLIN_F64  # noqa: E402
+
+__all__ = ["WN_PERLIN_F32", "WN_PERLIN_F64", "Context", "WaveletNoise", "PerlinNoise", "wavelet_texture", "noise_texture", "DataStats", "WnError",
            "default_context", "WN_EVAL_FAST", "WN_EVAL_EXACT", "WN_TILE_ODD_OFFSET", "pinned_empty"]
 
 
@@ -145,6 +147,26 @@ class Context:
     @property
     def last_kernel_ms(self):
         return float(lib.wn_timing_last_ms(self.h))
+
+    def time_main_kernel(self, on=True):
+        """Record one CUDA-event pair around the main kernel of every device-resident FAST lattice call (roofline)."""
+        check(lib.wn_timing_main_kernel_enable(self.h, 1 if on else 0))
+
+    def main_kernel_ms(self):
+        """Durations (ms) of the main kernels recorded since the last call; synchronises the stream."""
+        n = C.c_int()
+        buf = np.zeros(4096, np.float32)
+        check(lib.wn_timing_main_kernel_collect(self.h, C.c_void_p(buf.ctypes.data), buf.size, C.byref(n)))
+        return buf[:min(n.value, buf.size)].copy()
+
+    def axis_entries(self, coords, band_scale=1.0):
+        """(weights (n, 3) float32, first tap cell (n,) int32) of the FAST lattice kernels' axis table (diagnostics)."""
+        coords = np.ascontiguousarray(coords, np.float32)
+        w = np.empty((coords.size, 3), np.float32)
+        first = np.empty(coords.size, np.int32)
+        check(lib.wn_debug_axis_entries(self.h, C.c_void_p(coords.ctypes.data), coords.size, float(band_scale),
+                                        C.c_void_p(w.ctypes.data), C.c_void_p(first.ctypes.data)))
+        return w, first
 
     def stats(self, data):
         ptr, space, keep = _in(data)

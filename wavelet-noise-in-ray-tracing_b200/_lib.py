@@ -37,6 +37,9 @@ SIGNATURES = {
     "wn_version": (C.c_char_p, []),
     "wn_kernel_launches": (C.c_uint64, [vp]),
     "wn_timing_last_ms": (C.c_float, [vp]),
+    "wn_timing_main_kernel_enable": (C.c_int, [vp, C.c_int]),
+    "wn_timing_main_kernel_collect": (C.c_int, [vp, vp, C.c_int, C.POINTER(C.c_int)]),
+    "wn_debug_axis_entries": (C.c_int, [vp, vp, C.c_int, C.c_float, vp, vp]),
     "wn_debug_fold_plan": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, i32p, i32p,
                                      C.POINTER(C.c_int)]),
     "wn_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),

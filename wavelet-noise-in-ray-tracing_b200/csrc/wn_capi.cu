@@ -87,6 +87,10 @@ struct wn_ctx {
     size_t tev_used = 0;
     float last_ms = 0.0f;
     uint64_t launches = 0;
+    // optional per-call timing of the MAIN kernel of WN_DEVICE fast lattice calls (wn_timing_main_kernel_enable):
+    // one event pair per call, read back by wn_timing_main_kernel_collect after a synchronisation
+    bool time_main = false;
+    std::vector<cudaEvent_t> main_ev;    // pairs, in call order
 };
 
 struct DeviceGuard {
@@ -223,6 +227,7 @@ static void ctx_release(wn_ctx *c)
     if (c->ev_tile) cudaEventDestroy(c->ev_tile);
     if (c->side) cudaStreamDestroy(c->side);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->main_ev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->h2d) cudaStreamDestroy(c->h2d);
     if (c->d2h) cudaStreamDestroy(c->d2h);
@@ -264,6 +269,30 @@ extern "C" int wn_ctx_device(const wn_ctx *c, int *device, int *sm_count)
 
 extern "C" uint64_t wn_kernel_launches(const wn_ctx *c) { return c ? c->launches : 0; }
 extern "C" float wn_timing_last_ms(const wn_ctx *c) { return c ? c->last_ms : 0.0f; }
+
+extern "C" int wn_timing_main_kernel_enable(wn_ctx *c, int on)
+{
+    WN_REQUIRE(c, "wn_timing_main_kernel_enable: ctx is NULL");
+    c->time_main = on != 0;
+    return WN_OK;
+}
+
+extern "C" int wn_timing_main_kernel_collect(wn_ctx *c, float *ms, int capacity, int *count)
+{
+    WN_REQUIRE(c && count, "wn_timing_main_kernel_collect: NULL argument");
+    DeviceGuard g(c->device);
+    WN_CUDA(cudaStreamSynchronize(c->stream));
+    const int pairs = (int)(c->main_ev.size() / 2);
+    *count = pairs;
+    for (int i = 0; i < pairs; ++i) {
+        float t = 0.0f;
+        WN_CUDA(cudaEventElapsedTime(&t, c->main_ev[2 * i], c->main_ev[2 * i + 1]));
+        if (ms && i < capacity) ms[i] = t;
+    }
+    for (cudaEvent_t e : c->main_ev) cudaEventDestroy(e);
+    c->main_ev.clear();
+    return WN_OK;
+}
 
 extern "C" int wn_host_alloc(size_t bytes, void **out)
 {
@@ -892,9 +921,15 @@ extern "C" int wn_multiband3d_lattice(const wn_tile *t, const float *xs, int nx,
         WN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_side, 0));
         plan.pdl = pdl_side_main;
     }
-    if (space == WN_DEVICE)
+    if (space == WN_DEVICE) {
+        cudaEvent_t ta = nullptr, tb = nullptr;
+        if (c->time_main && cudaEventCreate(&ta) == cudaSuccess && cudaEventCreate(&tb) == cudaSuccess) {
+            c->main_ev.push_back(ta); c->main_ev.push_back(tb);
+            WN_CUDA(cudaEventRecord(ta, c->stream));
+        }
         r = run_device(c, [&](cudaStream_t st) { return wn_mb3d_fast_run(tv, L, ys, zs, b, nullptr, &plan, 0, nz, out, st); });
-    else {
+        if (tb) cudaEventRecord(tb, c->stream);
+    } else {
         // HOST: chunk by whole z slices so each chunk is a lattice slab
         size_t slices_per_chunk = std::max<size_t>(1, kChunkSamples / slice);
         ChunkIO io; io.out = out; io.out_item = slice * sizeof(float);
@@ -926,6 +961,30 @@ extern "C" int wn_debug_fold_plan(const float *xs, int nx, const float *ys, int 
     std::vector<float> ones((size_t)std::max(nbands, 1), 1.0f);
     if ((r = make_bands(band_scale, ones.data(), nbands, 1.0f, &b))) return r;
     *nfolded = wn_mb3d_fast_plan_host(xs, nx, ys, ny, zs, nz, b, tile_n, band_folded, block);
+    return WN_OK;
+}
+
+extern "C" int wn_debug_axis_entries(wn_ctx *c, const float *coords, int count, float band_scale, float *weights3,
+                                     int32_t *first_cell)
+{
+    WN_REQUIRE(c && coords && weights3 && first_cell, "wn_debug_axis_entries: NULL argument");
+    WN_REQUIRE(count > 0 && count <= (1 << 24), "wn_debug_axis_entries: count out of range");
+    DeviceGuard g(c->device);
+    float *dc = nullptr;
+    float4 *de = nullptr;
+    WN_CUDA(wn_scratch_alloc((void **)&dc, (size_t)count * sizeof(float), c->stream));
+    WN_CUDA(wn_scratch_alloc((void **)&de, (size_t)count * sizeof(float4), c->stream));
+    WN_CUDA(cudaMemcpyAsync(dc, coords, (size_t)count * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    c->launches += (uint64_t)wn_mb3d_debug_axis_table(dc, count, band_scale, de, c->stream);
+    std::vector<float4> h((size_t)count);
+    WN_CUDA(cudaMemcpyAsync(h.data(), de, (size_t)count * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    WN_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFreeAsync(dc, c->stream);
+    cudaFreeAsync(de, c->stream);
+    for (int i = 0; i < count; ++i) {
+        weights3[3 * i] = h[i].x; weights3[3 * i + 1] = h[i].y; weights3[3 * i + 2] = h[i].z;
+        std::memcpy(&first_cell[i], &h[i].w, sizeof(int32_t));
+    }
     return WN_OK;
 }
 

@@ -108,6 +108,9 @@ void wn_mb3d_fast_detach(WnFastPlan *plan, void **tab, void **P);
 int  wn_mb3d_fast_plan_host(const float *h_xs, int nx, const float *h_ys, int ny, const float *h_zs, int nz, WnBands b,
                             int tile_n, int *folded, int block[3]);
 
+// diagnostics: axis-table entries of `count` coordinates at one band scale (all device pointers); kernels launched
+int wn_mb3d_debug_axis_table(const float *coords, int count, float scale, float4 *entries, cudaStream_t st);
+
 // 3D tile -> x-padded replica (row pitch n+WN_TILE_PAD, the extra cells wrap around)
 int wn_launch_pad_tile(const float *N, float *Npad, int n, cudaStream_t st);
 

@@ -303,7 +303,13 @@ k_mb3d_brick(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, in
 
 // ---- pieces shared by the float4 kernels (k_mb3d_brick4, k_mb3d_col4): a CTA owns 128 x BY x BZ samples, lane l owns
 // x = 4l..4l+3.  Shared memory (float4 units): U[max_rows][32] | tables nbands x (128 + BY + BZ) | rowoff[max_rows] (int)
-struct Q4Foot { int ey[WN_MAX_BANDS], ez[WN_MAX_BANDS], row0[WN_MAX_BANDS + 1]; };
+struct Q4Foot {
+    int ey[WN_MAX_BANDS], ez[WN_MAX_BANDS], row0[WN_MAX_BANDS + 1];
+    // k_mb3d_rep: window advances of the first two bands at z step k in bits [2k, 2k+2) (planes entering the 3-deep
+    // window: first tap cell of step k minus that of step k-1); slow != 0 when some step advances by more than 3
+    unsigned long long adv[2];
+    int slow;
+};
 
 // axis-table entries of every band for this brick; ends with a barrier
 template <int BY, int BZ, int NT>
@@ -846,6 +852,20 @@ __device__ __forceinline__ void q4_footprints_rep(const float4 *s_tab, int nband
         }
         ft.row0[nbands] = row0;
     }
+    if (threadIdx.x < 32) {                                    // advance masks (BZ == 32 steps, one lane per step)
+        int slow = 0;
+        for (int b = 0; b < nbands && b < 2; ++b) {
+            const float4 *tZ = s_tab + b * PER_BAND + BX + BY;
+            const int k = threadIdx.x;
+            const int a = k == 0 ? 0 : __float_as_int(tZ[k].w) - __float_as_int(tZ[k - 1].w);
+            slow |= __any_sync(0xffffffffu, a > 3 || a < 0);
+            unsigned long long m = (unsigned long long)(a & 3) << (2 * k);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+            if (k == 0) ft.adv[b] = m;
+        }
+        if (threadIdx.x == 0) ft.slow = slow;
+    }
     __syncthreads();
     for (int b = 0; b < nbands; ++b) {
         const float4 *tY = s_tab + b * PER_BAND + BX, *tZ = tY + BY;
@@ -891,21 +911,34 @@ __device__ __forceinline__ void q4_xpass_rep(const float *__restrict__ N, int n,
         const float a10 = s1 ? 0.0f : t1.x, a11 = s1 ? t1.x : t1.y, a12 = s1 ? t1.y : t1.z, a13 = s1 ? t1.z : 0.0f;
         const float a20 = s2 ? 0.0f : t2.x, a21 = s2 ? t2.x : t2.y, a22 = s2 ? t2.y : t2.z, a23 = s2 ? t2.z : 0.0f;
         const float a30 = s3 ? 0.0f : t3.x, a31 = s3 ? t3.x : t3.y, a32 = s3 ? t3.y : t3.z, a33 = s3 ? t3.z : 0.0f;
-        for (int p = warp; p < pairs; p += NW) {
-            const int rr = (p >= half) + (R > 2 ? (p >= 2 * half) + (p >= 3 * half) : 0);
-            const float *base = (RX == 2 && (rr & 1)) ? base1 : base0;
-            const int r = row0 + 2 * p;
-            const int2 o = *reinterpret_cast<const int2 *>(s_rowoff + r);
+        // four rows (two pairs) per iteration: 16 independent tile loads in flight per lane
+        for (int p0 = warp; p0 < pairs; p0 += 2 * NW) {
+            float vv[4][4];
+            int rw[4];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float *q = base + (unsigned)(h ? o.y : o.x);
-                const float v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
+            for (int g = 0; g < 2; ++g) {
+                const int p = min(p0 + g * NW, pairs - 1);     // the tail repeats the last pair (same values rewritten)
+                const int rr = (p >= half) + (R > 2 ? (p >= 2 * half) + (p >= 3 * half) : 0);
+                const float *base = (RX == 2 && (rr & 1)) ? base1 : base0;
+                const int r = row0 + 2 * p;
+                const int2 o = *reinterpret_cast<const int2 *>(s_rowoff + r);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float *q = base + (unsigned)(h ? o.y : o.x);
+                    rw[2 * g + h] = r + h;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) vv[2 * g + h][e] = __ldg(q + e);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float v0 = vv[g][0], v1 = vv[g][1], v2 = vv[g][2], v3 = vv[g][3];
                 float4 u;
                 u.x = fmaf(a03, v3, fmaf(a02, v2, fmaf(a01, v1, a00 * v0)));
                 u.y = fmaf(a13, v3, fmaf(a12, v2, fmaf(a11, v1, a10 * v0)));
                 u.z = fmaf(a23, v3, fmaf(a22, v2, fmaf(a21, v1, a20 * v0)));
                 u.w = fmaf(a33, v3, fmaf(a32, v2, fmaf(a31, v1, a30 * v0)));
-                U4[(r + h) * 32 + lane] = u;
+                U4[rw[g] * 32 + lane] = u;
             }
         }
     } else {
@@ -1033,7 +1066,9 @@ k_mb3d_rep(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int 
     // per band: y weights, per replica the 3-deep window of y-contracted tile-z planes, the next plane to contract
     float4 ty[NB], v[NB][R][3];
     const float4 *unext[NB], *tZ[NB];
-    int slab4[NB], rstride[NB], mz0[NB], base[NB];
+    int slab4[NB], rstride[NB], prevw[NB];
+    unsigned long long advm[NB];
+    const bool slow = ft.slow != 0;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const float4 *tY = s_tab + b * PER_BAND + BX;
@@ -1041,7 +1076,8 @@ k_mb3d_rep(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int 
         ty[b] = tY[jl];
         slab4[b] = ft.ey[b] * 32;
         rstride[b] = b < NR ? (ft.row0[b + 1] - ft.row0[b]) / R * 32 : 0;
-        mz0[b] = __float_as_int(tZ[b][0].w);
+        prevw[b] = __float_as_int(tZ[b][0].w);
+        advm[b] = ft.adv[b];
         const float4 *u = U4 + ft.row0[b] * 32 + (__float_as_int(ty[b].w) - __float_as_int(tY[0].w)) * 32 + xq;
 #pragma unroll
         for (int r = 0; r < (b < NR ? R : 1); ++r)
@@ -1051,7 +1087,6 @@ k_mb3d_rep(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int 
                 v[b][r][f] = p4_contract3(ty[b].x, ty[b].y, ty[b].z, uu[0], uu[32], uu[64]);
             }
         unext[b] = u + 3 * slab4[b];
-        base[b] = 0;
     }
 
     const size_t plane = (size_t)nx * ny;
@@ -1062,10 +1097,12 @@ k_mb3d_rep(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int 
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             tz[b] = tZ[b][k];
-            const int rel = __float_as_int(tz[b].w) - mz0[b];
+            // planes entering the window at this step: from the brick's advance mask (no dependence on the table load
+            // above, so the branch does not wait for shared memory); steps of more than 3 cells take the table value
+            int adv = (int)(advm[b] >> (2 * k)) & 3;
+            if (slow) { adv = __float_as_int(tz[b].w) - prevw[b]; prevw[b] = __float_as_int(tz[b].w); }
 #pragma unroll 1
-            while (base[b] < rel) {
-                ++base[b];
+            for (; adv > 0; --adv) {
 #pragma unroll
                 for (int r = 0; r < (b < NR ? R : 1); ++r) {
                     const float4 *uu = unext[b] + r * rstride[b];
@@ -1631,6 +1668,21 @@ int brick_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsign
 // by the same kernels) and their block value, read by index mod period, is the start of every sample's running sum
 // (canonical summation, see band_value).  Detection is exact (bitwise on the table entries the device will compute),
 // so arbitrary coordinates simply do not fold.
+bool axis_replica_shift(const HostEntry *e, const int *first, int len, int *shift);
+
+// How the replica kernel (k_mb3d_rep) can treat a band on an nx x ny lattice: 0 = one window per sample column,
+// 1 = the x and y halves of the lattice are replicas (same weights, constant cell shift: four samples share the
+// period-block value), 2 = replicas that coincide (shift = whole tile periods: the band itself is shared by the four).
+int band_replica_class(const HostAxes &hax, int row, int nx, int ny)
+{
+    int sx = 0, sy = 0;
+    if (nx % 8 != 0 || ny % 2 != 0) return 0;
+    if (!axis_replica_shift(hax.ex(row), hax.fx(row), nx, &sx)) return 0;
+    if (!axis_replica_shift(hax.ey(row), hax.fy(row), ny, &sy)) return 0;
+    const bool same = hax.ex(row)[nx / 2].cell == hax.ex(row)[0].cell && hax.ey(row)[ny / 2].cell == hax.ey(row)[0].cell;
+    return same ? 2 : 1;
+}
+
 // smallest P <= len/2 with entry[i+P] == entry[i] for all i; len when the axis is not periodic
 int axis_period(const HostEntry *e, int len)
 {
@@ -1666,15 +1718,25 @@ FoldDecision decide_fold(const HostAxes &hax, const unsigned char *rows, const W
     // relative per-sample cost of evaluating a band directly, from its step in tile cells per sample (fitted to the
     // measured single-band times: 1 : 1.1 : 1.3 : 2 : 5.4 for steps 1/8 .. 2)
     double cost[WN_MAX_BANDS];
+    // typical step of an axis: the median of up to 15 evenly spaced consecutive differences (a block-cyclic z axis jumps
+    // at every chunk boundary; a single probe in the middle of the axis would land on such a jump)
     auto median_step = [](const float *a, int len, float scale) {
         if (len < 2) return 0.0;
-        const int m = len / 2;
-        return std::fabs(((double)a[m] - (double)a[m - 1]) * (double)scale);
+        double d[15];
+        const int probes = std::min(15, len - 1);
+        for (int q = 0; q < probes; ++q) {
+            const int m = 1 + (int)((long long)(len - 2) * q / std::max(1, probes - 1));
+            d[q] = std::fabs((double)a[m] - (double)a[m - 1]);
+        }
+        std::sort(d, d + probes);
+        return d[probes / 2] * (double)scale;
     };
+    double urows[WN_MAX_BANDS];                                // U rows of a 128 x 8 x 32 brick of the replica kernel
     for (int i = 0; i < b.nbands; ++i) {
-        const double st = std::max(median_step(h_xs, nx, b.scale[i]),
-                                   std::max(median_step(h_ys, ny, b.scale[i]), median_step(h_zs, nz, b.scale[i])));
+        const double sy = median_step(h_ys, ny, b.scale[i]), sz = median_step(h_zs, nz, b.scale[i]);
+        const double st = std::max(median_step(h_xs, nx, b.scale[i]), std::max(sy, sz));
         cost[i] = 1.0 + 1.2 * std::pow(st, 1.6);
+        urows[i] = std::ceil(8.0 * sy + 3.0) * std::ceil(32.0 * sz + 3.0);
     }
     // candidates: the folded bands must be a suffix of the canonical order (their block holds the canonical sum of that
     // suffix), so walk down from the highest scale and stop at the first band that does not repeat on this lattice
@@ -1693,6 +1755,23 @@ FoldDecision decide_fold(const HostAxes &hax, const unsigned char *rows, const W
     // in units of one band-sample (~1 ps of GPU time); level = the latency of one more small dependent launch (~8 us).
     double level_overhead = 8e6;
     if (const char *e = getenv("WN_FOLD_LEVEL_COST")) level_overhead = atof(e);   // tests fold tiny lattices with 0
+    // Per-sample cost of the bands left direct when the first nd canonical bands (lowest scales) stay direct:
+    // the sum of their costs plus 0.3 for adding the period-block value.  The replica kernel changes that for one or two
+    // direct bands on a lattice whose halves are replicas: the period-block value (and a coinciding higher band) is
+    // fetched / evaluated once per four samples (measured on config 3: bands 4 + 5 direct over a 256^3 block 0.85 ms,
+    // band 4 over a 512^3 block 0.98 ms, without sharing 1.04 / 1.11 ms).
+    int rclass[WN_MAX_BANDS];
+    for (int i = 0; i < b.nbands; ++i) rclass[i] = (i < 2 && nx % 4 == 0) ? band_replica_class(hax, rows[i], nx, ny) : 0;
+    auto direct_cost = [&](int nd, bool with_block) {
+        double sum = 0.0;
+        for (int i = 0; i < nd; ++i) sum += cost[i];
+        const double add = with_block ? 0.3 : 0.0;
+        // (only while the replicas' U rows fit the kernel's shared memory: rep_pass falls back otherwise)
+        if (nd == 1 && rclass[0] >= 1 && 4.0 * urows[0] <= 150.0) return cost[0] + 0.25 * add;
+        if (nd == 2 && rclass[0] >= 1 && rclass[1] == 2 && 4.0 * urows[0] + urows[1] <= 180.0) return cost[0] + 0.25 * (cost[1] + add);
+        if (nd == 2 && rclass[0] >= 1 && rclass[1] >= 1 && 2.0 * (urows[0] + urows[1]) <= 180.0) return sum + 0.5 * add;
+        return sum + add;
+    };
     double direct_sum = 0.0;
     for (int i = 0; i < b.nbands; ++i) direct_sum += cost[i];
     double best = direct_sum * (double)total, nested_sum = 0.0;
@@ -1707,8 +1786,11 @@ FoldDecision decide_fold(const HostAxes &hax, const unsigned char *rows, const W
         trial[cd.band] = true;
         ++ntrial;
         nested_sum += (cost[cd.band] + 0.3) * (double)(Lx * Ly * Lz) + level_overhead;
+        // a block that does not stay in L2 (> 32 MiB) is written to and read back from HBM: 8 bytes per block sample next
+        // to the 4 bytes per sample of the output stream the main kernel is bound by
+        if (Lx * Ly * Lz > (1LL << 23)) nested_sum += 2.0 * (double)(Lx * Ly * Lz);
         direct_sum -= cost[cd.band];
-        const double est = (direct_sum + 0.3) * (double)total + nested_sum;
+        const double est = direct_cost(b.nbands - ntrial, true) * (double)total + nested_sum;
         if (est < best) {
             best = est;
             for (int i = 0; i < b.nbands; ++i) folded[i] = trial[i];
@@ -1731,6 +1813,19 @@ void canonical_order(const WnBands &b, int order[WN_MAX_BANDS])
 }
 
 } // namespace
+
+// diagnostics: the axis-table entries {w0, w1, w2, first tap cell (unwrapped)} the lattice kernels use for `count`
+// coordinates of one axis at one band scale (device pointers), computed by the same kernel as in a real call
+int wn_mb3d_debug_axis_table(const float *coords, int count, float scale, float4 *entries, cudaStream_t st)
+{
+    if (count <= 0) return 0;
+    WnLattice c{coords, nullptr, nullptr, count, 0, 0};
+    WnBands b;
+    std::memset(&b, 0, sizeof(b));
+    b.nbands = 1; b.scale[0] = scale; b.weight[0] = 1.0f; b.post = 1.0f;
+    k_axis_tables<<<std::min((count + 255) / 256, 1184), 256, 0, st>>>(c, b, 0, 0, entries, nullptr, nullptr);
+    return 1;
+}
 
 int wn_launch_pad_tile(const float *N, float *Npad, int n, cudaStream_t st)
 {
