@@ -14,7 +14,8 @@
  *     wn_last_error() returns the message of the calling thread's last failure.
  *   - there is NO CPU fallback: without a CUDA device wn_ctx_create fails with WN_ENODEVICE.
  *   - one wn_ctx = one GPU + one stream; one host thread drives a context at a time.
- *     Multi-GPU = one process (or context) per GPU; samples shard with no exchange.
+ *     Multi-GPU = one process per GPU (bench.py under torchrun), or one wn_group in one process (below);
+ *     samples shard with no exchange.
  *   - `space` says where the caller's sample buffers live:
  *       WN_HOST   : host memory (pinned is faster).  The call copies in, computes, copies out and
  *                   returns after the result is in `out` (large lattices are chunked so the D2H of
@@ -240,6 +241,56 @@ int  wn_perlin_texture_values(const wn_perlin *pn, const float *p, size_t count,
 /* ---- statistics --------------------------------------------------------------------------------
  * replaces: WaveletNoise::calculateStats (cpp:268-288) without the printing (the host layer prints). */
 int  wn_stats_compute(wn_ctx *ctx, const float *data, size_t count, int space, wn_stats *out);
+
+/* ---- device groups: single-process multi-GPU -------------------------------------------------------
+ * north_star: volumes shard by z-slab and images by row-band across the GPUs of one box, each GPU holds a replica of
+ * the tile (broadcast once over NVLink with NCCL), output is gathered only for file write.  A wn_group owns one wn_ctx
+ * per GPU, driven by one host thread; sharded calls enqueue on every GPU before waiting for any, and there is no
+ * data-path collective (every sample reads only its GPU's tile replica).  The reference is single-threaded and has no
+ * counterpart; the loops that are sharded are experient/main.cpp:45-58 (volume, along z), :74-87 (projected plane, by
+ * row) and main.cpp:175-204 (render rows, through the batched texture hook).  NCCL is loaded at run time (libnccl.so.2)
+ * and only for groups of two or more GPUs. */
+typedef struct wn_group wn_group;
+typedef struct wn_gtile wn_gtile;
+#define WN_SHARD_SLAB    0   /* contiguous z-slabs / row-bands                                             */
+#define WN_SHARD_CYCLIC  1   /* volumes: 32-slice chunks dealt round-robin (every rank keeps the periodic
+                                structure of the whole volume, so per-rank work stays 1/N) */
+int  wn_group_create(int ngpus /* <= 0: all visible */, const int *devices /* NULL: 0..ngpus-1 */, wn_group **out);
+int  wn_group_destroy(wn_group *g);
+int  wn_group_size(const wn_group *g);
+int  wn_group_ctx(wn_group *g, int rank, wn_ctx **ctx);
+int  wn_group_synchronize(wn_group *g);
+/* one tile replica per GPU: rank 0 builds (wn_tile_build_seeded) or receives the coefficients, one ncclBroadcast
+ * replicates them on the ranks' streams */
+int  wn_group_tile_create(wn_group *g, int n, int dims, unsigned flags, wn_gtile **out);
+int  wn_group_tile_destroy(wn_gtile *t);
+int  wn_group_tile_build_seeded(wn_gtile *t, unsigned seed, unsigned long long *mt_draws);
+int  wn_group_tile_upload(wn_gtile *t, const float *N_host);
+int  wn_group_tile_rank(wn_gtile *t, int rank, wn_tile **tile);
+/* wn_multiband3d_lattice sharded along z (BASELINE config 3).  The shards stay on the devices (wn_group_shard); when
+ * out_host is not NULL the volume is also gathered there in the lattice layout (pinned memory recommended).  *gpu_ms
+ * (nullable) = max over the GPUs of the CUDA-event time of the enqueued kernels.  Results are bit-identical to the
+ * single-GPU call for either sharding (canonical summation, see wn_multiband3d_lattice). */
+int  wn_group_multiband3d_lattice(wn_gtile *t, const float *xs, int nx, const float *ys, int ny, const float *zs, int nz,
+                                  const float *band_scale, const float *weights, int nbands, float post_scale, int mode,
+                                  int sharding, float *out_host, float *gpu_ms);
+/* device buffer and float count of `rank`'s shard of the most recent sharded call */
+int  wn_group_shard(wn_group *g, int rank, float **dptr, size_t *count);
+/* wn_eval3d_projected_grid / wn_perlin_grid sharded into contiguous row-bands of the v axis (BASELINE config 4) */
+int  wn_group_eval3d_projected_grid(wn_gtile *t, const float origin[3], const float e1[3], const float *us, int nu,
+                                    const float e2[3], const float *vs, int nv, const float normal[3], float pre_scale,
+                                    float post_scale, float *out_host, float *gpu_ms);
+int  wn_group_perlin_grid(wn_group *g, wn_perlin *const *perlin_per_rank, const float origin[3], const float e1[3],
+                          const float *us, int nu, const float e2[3], const float *vs, int nv, float pre_scale,
+                          float *out_host, float *gpu_ms);
+/* wn_wavelet_texture_values with the points cut into one contiguous run per GPU (BASELINE config 5: the hit points of a
+ * row band).  Copies in, kernels and copies out of all GPUs are in flight together; wait == 0 returns after enqueueing
+ * (wn_group_synchronize before reading grey_host), so the caller can trace the next band meanwhile. */
+int  wn_group_wavelet_texture_values(wn_gtile *t, const float *p_host, size_t count, double scale, int octave,
+                                     float *grey_host, int wait);
+
+int  wn_group_perlin_texture_values(wn_group *g, wn_perlin *const *perlin_per_rank, const float *p_host, size_t count,
+                                    double scale, int octave, float *grey_host, int wait);
 
 #ifdef __cplusplus
 }

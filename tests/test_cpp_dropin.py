@@ -17,7 +17,7 @@ BIN = os.path.join(CPP, "bin")
 
 def test_cpp_layer_builds_and_reference_driver_links():
     subprocess.run(["make", "-s", "-C", CPP, "all"], check=True)
-    for exe in ("experiment_b200", "dropin_selftest"):
+    for exe in ("experiment_b200", "dropin_selftest", "sharded_b200"):
         assert os.access(os.path.join(BIN, exe), os.X_OK)
     if os.path.isdir("/root/reference/experient"):
         subprocess.run(["make", "-s", "-C", CPP, "reference_dropin"], check=True)
@@ -91,6 +91,31 @@ def test_cpp_scalar_surface_matches_oracle(oracle):
     assert f("perlin2d") == np.float32(oracle.perlin_noise(perm, np.float32(0.3), np.float32(0.7), 0.0))
     assert f("tex0") == np.float32(oracle.wavelet_texture_value(tile, 128, [0.5, 1.5, -2.25], 1.0, 4))
     assert f("tex1") == np.float32(oracle.wavelet_texture_value(tile, 128, [9.0, 9.5, 10.25], 1.0, 4))
+
+
+@pytest.mark.gpu
+def test_sharded_cpp_drivers_are_gpu_count_invariant():
+    """cpp/sharded_main.cpp (C ABI device groups): config 3 at 256^3 and config 4 at 512^2 produce the same output hash
+    for every GPU count on this box and for both z shardings."""
+    import json
+    import torch
+    exe = os.path.join(BIN, "sharded_b200")
+    counts = [k for k in (1, 2, 4, 8) if k <= torch.cuda.device_count()]
+    vol, plane = set(), set()
+    for n in counts:
+        for sharding in ("cyclic", "slab"):
+            r = subprocess.run([exe, "volume", "--gpus", str(n), "--size", "256", "--reps", "2", "--gather", "--sharding",
+                                sharding], capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-1000:]
+            line = json.loads(r.stdout.strip().splitlines()[-1])
+            assert line["n_gpus"] == n and line["gsamples_s"] > 0
+            vol.add(line["fnv1a64"])
+        r = subprocess.run([exe, "plane", "--gpus", str(n), "--size", "512", "--reps", "1"], capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 0, r.stderr[-1000:]
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        plane.add((line["fnv1a64_projected"], line["fnv1a64_perlin"]))
+    assert len(vol) == 1 and len(plane) == 1, (vol, plane)
 
 
 @pytest.mark.gpu

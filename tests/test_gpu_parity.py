@@ -653,3 +653,47 @@ def test_config3_full_size_1024_cubed(wn, oracle, gpu_tiles, tiles128):
         assert abs(mean) < 0.01 and 0.4 < var < 0.7, (mean, var)
     finally:
         t.ctx.set_stream(None)
+
+
+# ---------------------------------------------------------------------------------------------
+# device groups (single-process multi-GPU over the C ABI); N > 1 needs a multi-GPU box
+# ---------------------------------------------------------------------------------------------
+def _group_sizes():
+    import torch
+    n = torch.cuda.device_count()
+    return [k for k in (1, 2, 4, 8) if k <= n]
+
+
+def test_device_group_matches_single_context(wn, oracle, gpu_tiles, tiles128):
+    """wn_group: tile built on rank 0 and replicated (NCCL broadcast when N > 1), config 3 sharded along z (block-cyclic
+    and contiguous slabs), config 4 by row-band, config 5 points by contiguous runs -- every GPU count available on this
+    box must reproduce the single-context results BIT FOR BIT (samples are independent; FAST sums canonically)."""
+    t = gpu_tiles[3]
+    ax = lattice_axis(np.arange(1024))
+    xs, ys, zs = ax[:256], ax[:256], ax[:320]
+    want = t.multiband3D_lattice(xs, ys, zs, BANDS, WEIGHTS, float(POST))
+    f = np.float32
+    nrm = (np.array([1, 2, 3], np.float64) / np.sqrt(14.0)).astype(f)
+    e1 = (np.array([2, -1, 0], np.float64) / np.sqrt(5.0)).astype(f)
+    e2 = (np.array([3, 6, -5], np.float64) / np.sqrt(70.0)).astype(f)
+    origin = np.array([0, 0, 1], f)
+    us, vs = ax[:96], ax[100:181]
+    want_proj = t.evaluate3DProjected_grid(origin, e1, us, e2, vs, nrm, 32.0, 1.5)
+    pts = np.random.RandomState(3).uniform(-10, 10, (5001, 3)).astype(f)
+    want_tex = t.texture_values(pts, 1.0, 4)
+    for n in _group_sizes():
+        g = wn.DeviceGroup(n)
+        assert g.size == n
+        gt = g.tile(128, 3, 12345)
+        for sharding in (wn.WN_SHARD_CYCLIC, wn.WN_SHARD_SLAB):
+            got, ms = gt.multiband3D_lattice(xs, ys, zs, BANDS, WEIGHTS, float(POST), sharding=sharding)
+            assert_bits(got, want, f"group of {n}, sharding {sharding}")
+            assert ms > 0.0
+        exact, _ = gt.multiband3D_lattice(xs[:64], ys[:64], zs[:70], BANDS, WEIGHTS, float(POST), mode=wn.WN_EVAL_EXACT,
+                                          sharding=wn.WN_SHARD_SLAB)
+        assert_bits(exact, oracle.multiband3d_lattice(tiles128[3], 128, xs[:64], ys[:64], zs[:70], BANDS, WEIGHTS, POST),
+                    f"group of {n}, exact")
+        got, _ = gt.evaluate3DProjected_grid(origin, e1, us, e2, vs, nrm, 32.0, 1.5)
+        assert_bits(got, want_proj, f"group of {n}, projected row-bands")
+        assert_bits(gt.texture_values(pts, 1.0, 4), want_tex, f"group of {n}, texture points")
+        g.close()

@@ -30,7 +30,9 @@ from ._lib import (WN_DEVICE, WN_EVAL_EXACT, WN_EVAL_FAST, WN_HOST, WN_TILE_DEFA
 
 from ._lib import WN_PERLIN_F32, WN_PERLIN_F64  # noqa: E402
 
-__all__ = ["WN_PERLIN_F32", "WN_PERLIN_F64", "Context", "WaveletNoise", "PerlinNoise", "wavelet_texture", "noise_texture", "DataStats", "WnError",
+from ._lib import WN_SHARD_CYCLIC, WN_SHARD_SLAB  # noqa: E402
+
+__all__ = ["WN_PERLIN_F32", "WN_PERLIN_F64", "WN_SHARD_CYCLIC", "WN_SHARD_SLAB", "DeviceGroup", "GroupTile", "Context", "WaveletNoise", "PerlinNoise", "wavelet_texture", "noise_texture", "DataStats", "WnError",
            "default_context", "WN_EVAL_FAST", "WN_EVAL_EXACT", "WN_TILE_ODD_OFFSET", "pinned_empty"]
 
 
@@ -564,6 +566,104 @@ class PerlinNoise:
         optr, out = _out(out, (count,), space, keep if _is_torch(keep) else None)
         check(lib.wn_perlin_texture_values(self.h, C.c_void_p(ptr), count, float(scale), int(octave), C.c_void_p(optr),
                                            space))
+        return out
+
+
+class DeviceGroup:
+    """Single-process multi-GPU group (wn_group): one context per GPU, tile replicated with one NCCL broadcast, sharded
+    evaluation calls that enqueue on every GPU before waiting for any.  ngpus <= 0: every visible GPU."""
+
+    def __init__(self, ngpus=0, devices=None):
+        h = C.c_void_p()
+        dev = None
+        if devices is not None:
+            dev = (C.c_int * len(devices))(*devices)
+            ngpus = len(devices)
+        check(lib.wn_group_create(int(ngpus), dev, C.byref(h)))
+        self.h = h
+        self.size = lib.wn_group_size(self.h)
+        self._tiles = weakref.WeakSet()
+
+    def close(self):
+        if getattr(self, "h", None):
+            for t in list(self._tiles):
+                t.close()
+            lib.wn_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(lib.wn_group_synchronize(self.h))
+
+    def tile(self, n, dims=3, seed=0, flags=WN_TILE_DEFAULT, coefficients=None):
+        """A tile replicated on every GPU of the group: built from `seed` on rank 0 (GPU fill + filters) or uploaded
+        from `coefficients`, then broadcast."""
+        return GroupTile(self, n, dims, seed, flags, coefficients)
+
+
+class GroupTile:
+    def __init__(self, group, n, dims, seed, flags, coefficients):
+        self.group = group
+        h = C.c_void_p()
+        check(lib.wn_group_tile_create(group.h, int(n), int(dims), int(flags), C.byref(h)))
+        self.h = h
+        group._tiles.add(self)
+        if coefficients is None:
+            check(lib.wn_group_tile_build_seeded(self.h, int(seed) & 0xFFFFFFFF, None))
+        else:
+            c = np.ascontiguousarray(coefficients, np.float32)
+            check(lib.wn_group_tile_upload(self.h, C.c_void_p(c.ctypes.data)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            if getattr(self.group, "h", None):
+                lib.wn_group_tile_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def multiband3D_lattice(self, xs, ys, zs, band_scale, weights, post_scale=1.0, mode=WN_EVAL_FAST,
+                            sharding=_lib.WN_SHARD_CYCLIC, gather=True):
+        """Returns (volume or None, gpu_ms): the volume gathered on the host when gather is true (the shards stay on the
+        devices either way), gpu_ms = max over the GPUs of the CUDA-event time."""
+        xs, ys, zs = _host(xs), _host(ys), _host(zs)
+        bs, w = _host(band_scale), _host(weights)
+        if bs.size != w.size:
+            raise ValueError("band_scale and weights differ in length")
+        out = np.empty((zs.size, ys.size, xs.size), np.float32) if gather else None
+        ms = C.c_float()
+        check(lib.wn_group_multiband3d_lattice(self.h, C.c_void_p(xs.ctypes.data), xs.size, C.c_void_p(ys.ctypes.data),
+                                               ys.size, C.c_void_p(zs.ctypes.data), zs.size, C.c_void_p(bs.ctypes.data),
+                                               C.c_void_p(w.ctypes.data), bs.size, float(post_scale), int(mode),
+                                               int(sharding), C.c_void_p(out.ctypes.data) if gather else None,
+                                               C.byref(ms)))
+        return out, ms.value
+
+    def evaluate3DProjected_grid(self, origin, e1, us, e2, vs, normal, pre_scale=1.0, post_scale=1.0, gather=True):
+        o, a, b, us, vs, nv = _host(origin), _host(e1), _host(e2), _host(us), _host(vs), _host(normal)
+        out = np.empty((vs.size, us.size), np.float32) if gather else None
+        ms = C.c_float()
+        check(lib.wn_group_eval3d_projected_grid(self.h, C.c_void_p(o.ctypes.data), C.c_void_p(a.ctypes.data),
+                                                 C.c_void_p(us.ctypes.data), us.size, C.c_void_p(b.ctypes.data),
+                                                 C.c_void_p(vs.ctypes.data), vs.size, C.c_void_p(nv.ctypes.data),
+                                                 float(pre_scale), float(post_scale),
+                                                 C.c_void_p(out.ctypes.data) if gather else None, C.byref(ms)))
+        return out, ms.value
+
+    def texture_values(self, pts, scale, octave):
+        pts = np.ascontiguousarray(pts, np.float32)
+        out = np.empty(pts.size // 3, np.float32)
+        check(lib.wn_group_wavelet_texture_values(self.h, C.c_void_p(pts.ctypes.data), pts.size // 3, float(scale),
+                                                  int(octave), C.c_void_p(out.ctypes.data), 1))
         return out
 
 

@@ -13,6 +13,7 @@ WN_HOST, WN_DEVICE = 0, 1
 WN_TILE_DEFAULT, WN_TILE_ODD_OFFSET = 0, 1
 WN_EVAL_FAST, WN_EVAL_EXACT = 0, 1
 WN_PERLIN_F64, WN_PERLIN_F32 = 0, 1
+WN_SHARD_SLAB, WN_SHARD_CYCLIC = 0, 1
 WN_ENODEVICE = -2
 
 f32p = C.POINTER(C.c_float)
@@ -85,6 +86,25 @@ SIGNATURES = {
     "wn_wavelet_texture2d_values": (C.c_int, [vp, vp, C.c_size_t, C.c_double, C.c_int, vp, C.c_int]),
     "wn_perlin_texture_values": (C.c_int, [vp, vp, C.c_size_t, C.c_double, C.c_int, vp, C.c_int]),
     "wn_stats_compute": (C.c_int, [vp, vp, C.c_size_t, C.c_int, C.POINTER(WnStats)]),
+    "wn_group_create": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
+    "wn_group_destroy": (C.c_int, [vp]),
+    "wn_group_size": (C.c_int, [vp]),
+    "wn_group_ctx": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "wn_group_synchronize": (C.c_int, [vp]),
+    "wn_group_tile_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_uint, C.POINTER(vp)]),
+    "wn_group_tile_destroy": (C.c_int, [vp]),
+    "wn_group_tile_build_seeded": (C.c_int, [vp, C.c_uint, C.POINTER(C.c_ulonglong)]),
+    "wn_group_tile_upload": (C.c_int, [vp, vp]),
+    "wn_group_tile_rank": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "wn_group_multiband3d_lattice": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_float,
+                                               C.c_int, C.c_int, vp, C.POINTER(C.c_float)]),
+    "wn_group_shard": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+    "wn_group_eval3d_projected_grid": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_float, C.c_float, vp,
+                                                 C.POINTER(C.c_float)]),
+    "wn_group_perlin_grid": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_float, vp,
+                                       C.POINTER(C.c_float)]),
+    "wn_group_wavelet_texture_values": (C.c_int, [vp, vp, C.c_size_t, C.c_double, C.c_int, vp, C.c_int]),
+    "wn_group_perlin_texture_values": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_double, C.c_int, vp, C.c_int]),
 }
 
 

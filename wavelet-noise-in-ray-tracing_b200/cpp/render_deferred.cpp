@@ -7,16 +7,19 @@
 //   pass 1 (CPU, unchanged reference geometry code): for a band of image rows, trace every sample in the reference's
 //           loop order; a recording texture notes each hit point instead of evaluating the noise, and each sample keeps
 //           its chain of attenuation factors (constant colour | lookup #i) and its terminal radiance;
-//   pass 2 (GPU): ONE batched call per band evaluates all recorded lookups
-//           (wn_wavelet_texture_values / wn_perlin_texture_values = texture.h:67-107 / :37-43, bit-exact);
+//   pass 2 (GPUs): ONE batched call per band evaluates all recorded lookups
+//           (wn_group_wavelet_texture_values / wn_group_perlin_texture_values = texture.h:67-107 / :37-43, bit-exact);
+//           with --gpus G the band's points are cut into G contiguous runs, one per GPU, all in flight together;
 //   pass 3 (CPU): each sample's product is re-formed right to left exactly like `attenuation * trace(...)`
 //           (main.cpp:55), summed per pixel in sample order and quantised with the reference's expression.
+// The passes are software-pipelined over the bands: the GPUs shade band k (from pinned staging, enqueue-only call)
+// while the CPU recombines band k-1 and traces band k+1, so the noise path costs no wall time next to the tracer.
 // The PNG/PPM are byte-identical to the reference's (tests compare with result_raytracing/*.png).
 //
 // This file contains no reference code: the RTIOW substrate (vec3/ray/sphere/quad/material ..., CC0) and
 // stb_image_write.h are #included from the reference tree where it lies (-I$(REF)) at build time, like oracle/_ref.
 // Protocol kept from the reference: noise type and octave are read from stdin (main.cpp:85-109).
-// Extra argv: --width W --height H --spp S --band ROWS --out DIR --gpus G (one context per GPU, bands round-robin).
+// Extra argv: --width W --height H --spp S --band ROWS --out DIR --gpus G (one device group of G GPUs).
 #define STB_IMAGE_WRITE_IMPLEMENTATION
 #include "stb_image_write.h"
 
@@ -78,10 +81,28 @@ void die(int rc)
     }
 }
 
-struct Gpu {
-    wn_ctx* ctx = nullptr;
-    wn_tile* tile = nullptr;
-    wn_perlin* perlin = nullptr;
+// pinned host staging that grows on demand (the lookups of a band go to the GPUs from here, the grey values come back)
+struct Pinned {
+    float* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n)
+    {
+        if (n <= cap) return;
+        if (p) wn_host_free(p);
+        cap = n + n / 4 + 1024;
+        die(wn_host_alloc(cap * sizeof(float), (void**)&p));
+    }
+    ~Pinned() { if (p) wn_host_free(p); }
+};
+
+// everything pass 3 needs about one band of rows
+struct Band {
+    int jtop = 0, jbot = 0;
+    std::vector<Factor> factors;                // all chains of the band, concatenated
+    std::vector<int> chain_begin;               // per sample: first factor
+    std::vector<color> terminal;                // per sample: innermost radiance
+    Pinned points, grey;
+    size_t nlook = 0;
 };
 
 }  // namespace
@@ -113,16 +134,21 @@ int main(int argc, char** argv)
     const double tex_scale = 1.0;               // create_noise_texture(selected_noise, 1.0, octave_level), main.cpp:144
 
     // ---- GPU side: the texture's noise objects (texture.h:53-65 builds n=128 seed 12345; texture.h:46 default-seeds perlin)
-    std::vector<Gpu> gpus(ngpus);
-    for (int g = 0; g < ngpus; ++g) {
-        die(wn_ctx_create(g, &gpus[g].ctx));
-        if (wavelet) {
-            die(wn_tile_create(gpus[g].ctx, 128, 3, WN_TILE_DEFAULT, &gpus[g].tile));
-            die(wn_tile_build_seeded(gpus[g].tile, 12345, nullptr));
-        } else {
-            int32_t perm[512];
-            die(wn_perlin_make_perm(5489u, perm));      // std::mt19937::default_seed
-            die(wn_perlin_create(gpus[g].ctx, perm, &gpus[g].perlin));
+    wn_group* group = nullptr;
+    die(wn_group_create(ngpus, nullptr, &group));
+    ngpus = wn_group_size(group);
+    wn_gtile* gtile = nullptr;
+    std::vector<wn_perlin*> perlins(ngpus, nullptr);
+    if (wavelet) {
+        die(wn_group_tile_create(group, 128, 3, WN_TILE_DEFAULT, &gtile));
+        die(wn_group_tile_build_seeded(gtile, 12345, nullptr));      // rank 0 builds, one NCCL broadcast replicates
+    } else {
+        int32_t perm[512];
+        die(wn_perlin_make_perm(5489u, perm));                       // std::mt19937::default_seed
+        for (int g = 0; g < ngpus; ++g) {
+            wn_ctx* c = nullptr;
+            die(wn_group_ctx(group, g, &c));
+            die(wn_perlin_create(c, perm, &perlins[g]));
         }
     }
 
@@ -147,22 +173,48 @@ int main(int argc, char** argv)
     file << "P3\n" << width << " " << height << "\n255\n";
     std::cout << "Processing " << width << "x" << height << " @ " << spp << " spp, " << noise_name << std::endl;
 
-    // per band buffers
-    std::vector<Factor> factors;                // all chains of the band, concatenated
-    std::vector<int> chain_begin;               // per sample: first factor
-    std::vector<color> terminal;                // per sample: innermost radiance
-    std::vector<float> grey;
+    Band bands[2];                              // double buffer: the GPUs work on one band while the CPU fills the other
     size_t total_lookups = 0;
-    double t_trace = 0, t_gpu = 0, t_combine = 0;
-    int band_index = 0;
+    double t_trace = 0, t_wait = 0, t_combine = 0;
+    const auto t_start = std::chrono::steady_clock::now();
 
+    // pass 3 of a band whose grey values have arrived
+    auto combine = [&](Band& B) {
+        size_t sample = 0;
+        const float* grey = B.grey.p;
+        for (int j = B.jtop; j >= B.jbot; --j)
+            for (int i = 0; i < width; ++i) {
+                vec3 color_sum(0, 0, 0);
+                for (int s = 0; s < spp; ++s, ++sample) {
+                    color c = B.terminal[sample];
+                    for (int f = B.chain_begin[sample + 1] - 1; f >= B.chain_begin[sample]; --f) {
+                        const Factor& fa = B.factors[f];
+                        const color att = fa.lookup >= 0 ? color(grey[fa.lookup], grey[fa.lookup], grey[fa.lookup]) : fa.constant;
+                        c = att * c;
+                    }
+                    color_sum += c;
+                }
+                vec3 c = color_sum / float(spp);
+                int r = static_cast<int>(255.99 * clamp01(c.x(), 0.0f, 1.0f));
+                int g = static_cast<int>(255.99 * clamp01(c.y(), 0.0f, 1.0f));
+                int b = static_cast<int>(255.99 * clamp01(c.z(), 0.0f, 1.0f));
+                file << r << " " << g << " " << b << "\n";
+                int index = ((height - 1 - j) * width + i) * 3;
+                image[index + 0] = r; image[index + 1] = g; image[index + 2] = b;
+            }
+    };
+
+    int band_index = 0;
+    Band* in_flight = nullptr;                  // band whose lookups are on the GPUs
     for (int jtop = height - 1; jtop >= 0; jtop -= band_rows, ++band_index) {
-        const int jbot = std::max(jtop - band_rows + 1, 0);
+        Band& B = bands[band_index & 1];
+        B.jtop = jtop;
+        B.jbot = std::max(jtop - band_rows + 1, 0);
         auto c0 = std::chrono::steady_clock::now();
         // ---------------- pass 1: trace in the reference's loop order (rows top -> bottom, x, samples), main.cpp:175-191
         g_rec.clear();
-        factors.clear(); chain_begin.clear(); terminal.clear();
-        for (int j = jtop; j >= jbot; --j)
+        B.factors.clear(); B.chain_begin.clear(); B.terminal.clear();
+        for (int j = B.jtop; j >= B.jbot; --j)
             for (int i = 0; i < width; ++i)
                 for (int s = 0; s < spp; ++s) {
                     float rand_u = float(rand()) / RAND_MAX - 0.5f;
@@ -170,7 +222,7 @@ int main(int argc, char** argv)
                     float u = float(i + 0.5f + rand_u) / width;
                     float v = float(j + 0.5f + rand_v) / height;
                     ray r(origin, unit_vector(lower_left_corner + u * horizontal + v * vertical - origin));
-                    chain_begin.push_back((int)factors.size());
+                    B.chain_begin.push_back((int)B.factors.size());
                     // iterative form of trace() (main.cpp:38-59); same calls in the same order
                     color last(0, 0, 0);
                     for (int step = 0;; ++step) {
@@ -186,62 +238,57 @@ int main(int argc, char** argv)
                         ray scattered;
                         g_rec.last = -1;
                         if (rec.mat->scatter(r, rec, attenuation, scattered)) {
-                            factors.push_back(Factor{g_rec.last, attenuation});
+                            B.factors.push_back(Factor{g_rec.last, attenuation});
                             r = scattered;
                             continue;
                         }
                         last = rec.mat->emitted(rec.u, rec.v, rec.p);
                         break;
                     }
-                    terminal.push_back(last);
+                    B.terminal.push_back(last);
                 }
-        chain_begin.push_back((int)factors.size());
+        B.chain_begin.push_back((int)B.factors.size());
+        B.nlook = g_rec.points.size() / 3;
+        B.points.ensure(3 * B.nlook);
+        B.grey.ensure(B.nlook);
+        if (B.nlook) std::memcpy(B.points.p, g_rec.points.data(), 3 * B.nlook * sizeof(float));
+        total_lookups += B.nlook;
         auto c1 = std::chrono::steady_clock::now();
 
-        // ---------------- pass 2: one batched GPU evaluation of the band's lookups
-        const size_t nlook = g_rec.points.size() / 3;
-        grey.resize(nlook);
-        Gpu& G = gpus[band_index % ngpus];
-        if (nlook) {
-            if (wavelet) die(wn_wavelet_texture_values(G.tile, g_rec.points.data(), nlook, tex_scale, octave_level, grey.data(), WN_HOST));
-            else die(wn_perlin_texture_values(G.perlin, g_rec.points.data(), nlook, tex_scale, octave_level, grey.data(), WN_HOST));
-        }
-        total_lookups += nlook;
+        // ---------------- pass 2: the previous band's batch ran during this trace; wait for it (normally already done),
+        // hand this band to the GPUs (enqueue only), then recombine the previous band while they work
+        die(wn_group_synchronize(group));
         auto c2 = std::chrono::steady_clock::now();
-
-        // ---------------- pass 3: re-form the products right to left, accumulate, quantise (main.cpp:55, 190-202)
-        size_t sample = 0;
-        for (int j = jtop; j >= jbot; --j)
-            for (int i = 0; i < width; ++i) {
-                vec3 color_sum(0, 0, 0);
-                for (int s = 0; s < spp; ++s, ++sample) {
-                    color c = terminal[sample];
-                    for (int f = chain_begin[sample + 1] - 1; f >= chain_begin[sample]; --f) {
-                        const Factor& fa = factors[f];
-                        const color att = fa.lookup >= 0 ? color(grey[fa.lookup], grey[fa.lookup], grey[fa.lookup]) : fa.constant;
-                        c = att * c;
-                    }
-                    color_sum += c;
-                }
-                vec3 c = color_sum / float(spp);
-                int r = static_cast<int>(255.99 * clamp01(c.x(), 0.0f, 1.0f));
-                int g = static_cast<int>(255.99 * clamp01(c.y(), 0.0f, 1.0f));
-                int b = static_cast<int>(255.99 * clamp01(c.z(), 0.0f, 1.0f));
-                file << r << " " << g << " " << b << "\n";
-                int index = ((height - 1 - j) * width + i) * 3;
-                image[index + 0] = r; image[index + 1] = g; image[index + 2] = b;
-            }
+        if (B.nlook) {
+            if (wavelet) die(wn_group_wavelet_texture_values(gtile, B.points.p, B.nlook, tex_scale, octave_level, B.grey.p, 0));
+            else die(wn_group_perlin_texture_values(group, perlins.data(), B.points.p, B.nlook, tex_scale, octave_level, B.grey.p, 0));
+        }
+        // ---------------- pass 3 (previous band): products right to left, accumulate, quantise (main.cpp:55, 190-202)
+        if (in_flight) combine(*in_flight);
+        in_flight = &B;
         auto c3 = std::chrono::steady_clock::now();
         t_trace += std::chrono::duration<double>(c1 - c0).count();
-        t_gpu += std::chrono::duration<double>(c2 - c1).count();
+        t_wait += std::chrono::duration<double>(c2 - c1).count();
         t_combine += std::chrono::duration<double>(c3 - c2).count();
     }
+    {
+        auto c1 = std::chrono::steady_clock::now();
+        die(wn_group_synchronize(group));
+        auto c2 = std::chrono::steady_clock::now();
+        if (in_flight) combine(*in_flight);
+        t_wait += std::chrono::duration<double>(c2 - c1).count();
+        t_combine += std::chrono::duration<double>(std::chrono::steady_clock::now() - c2).count();
+    }
+    const double t_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     stbi_write_png(output_png.c_str(), width, height, 3, image.data(), width * 3);
 
     std::printf("texture lookups: %zu (%.3f per primary ray)\n", total_lookups, (double)total_lookups / ((double)width * height * spp));
-    std::printf("time: trace(CPU) %.3f s, noise batches (GPU incl. copies) %.3f s, recombine %.3f s\n", t_trace, t_gpu, t_combine);
-    if (t_gpu > 0) std::printf("noise-sampling path: %.1f Mlookups/s through the host API\n", total_lookups / t_gpu / 1e6);
+    std::printf("time: total %.3f s = trace(CPU) %.3f s + recombine(CPU) %.3f s + waiting for the GPUs %.3f s (%d GPU%s, "
+                "noise batches overlap the tracing of the next band)\n", t_total, t_trace, t_combine, t_wait, ngpus, ngpus == 1 ? "" : "s");
+    if (t_wait > 0) std::printf("noise-sampling path: %.1f Mlookups/s of exposed GPU time\n", total_lookups / t_wait / 1e6);
     std::cout << "- PPM: " << output_ppm << "\n- PNG: " << output_png << std::endl;
-    for (Gpu& G : gpus) { wn_tile_destroy(G.tile); wn_perlin_destroy(G.perlin); wn_ctx_destroy(G.ctx); }
+    for (wn_perlin* p : perlins) wn_perlin_destroy(p);
+    wn_group_tile_destroy(gtile);
+    wn_group_destroy(group);
     return 0;
 }

@@ -18,7 +18,8 @@ ${NVCC} ${COMMON} ${PTXAS_V} -fmad=false -c "${HERE}/wn_eval_exact.cu"     -o "$
 ${NVCC} ${COMMON} ${PTXAS_V}             -c "${HERE}/wn_multiband_fast.cu" -o "${BUILD}/wn_multiband_fast.o"
 ${NVCC} ${COMMON} ${PTXAS_V} -fmad=false -c "${HERE}/wn_rng.cu"            -o "${BUILD}/wn_rng.o"
 ${NVCC} ${COMMON}               -fmad=false -c "${HERE}/wn_capi.cu"         -o "${BUILD}/wn_capi.o"
+${NVCC} ${COMMON}               -fmad=false -c "${HERE}/wn_group.cu"        -o "${BUILD}/wn_group.o"
 ${NVCC} ${ARCH} -shared -ccbin /usr/bin/g++ -o "${OUT}/libwn_b200.so" \
-    "${BUILD}/wn_tilegen.o" "${BUILD}/wn_eval_exact.o" "${BUILD}/wn_multiband_fast.o" "${BUILD}/wn_rng.o" "${BUILD}/wn_capi.o" \
-    -cudart static
+    "${BUILD}/wn_tilegen.o" "${BUILD}/wn_eval_exact.o" "${BUILD}/wn_multiband_fast.o" "${BUILD}/wn_rng.o" "${BUILD}/wn_capi.o" "${BUILD}/wn_group.o" \
+    -cudart static -ldl
 echo "built ${OUT}/libwn_b200.so"

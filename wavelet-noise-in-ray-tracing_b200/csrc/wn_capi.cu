@@ -46,6 +46,16 @@ static int wn_fail(int code, const char *fmt, ...)
         if (!(cond)) return wn_fail(WN_EINVAL, __VA_ARGS__);                                       \
     } while (0)
 
+// used by the other host translation units (wn_group.cu)
+int wn_set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
 extern "C" const char *wn_last_error(void) { return g_err; }
 extern "C" const char *wn_version(void) { return "wn_b200 0.1 (sm_100a)"; }
 
@@ -243,6 +253,8 @@ extern "C" int wn_ctx_destroy(wn_ctx *c)
     ctx_release(c);
     return WN_OK;
 }
+
+cudaStream_t wn_ctx_stream_internal(const wn_ctx *c) { return c->stream; }
 
 extern "C" int wn_ctx_set_stream(wn_ctx *c, void *s)
 {
