@@ -13,6 +13,12 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-ffp-contract=off -ccbin /usr/bin/g++ ${ARCH}"
 mkdir -p "${BUILD}"
 PTXAS_V="${WN_PTXAS_V:+-Xptxas -v}"
+# MT19937 jump-ahead tables of wn_rng.cu: generated (and self-checked) by tools/gen_mt_jump_tables.py, ~7 s, cached
+GEN="${HERE}/../../tools/gen_mt_jump_tables.py"
+if [ ! -s "${BUILD}/wn_mt_jump_tables.inc" ] || [ "${GEN}" -nt "${BUILD}/wn_mt_jump_tables.inc" ]; then
+    "${PYTHON:-python3}" "${GEN}" --check > "${BUILD}/wn_mt_jump_tables.inc.tmp"
+    mv "${BUILD}/wn_mt_jump_tables.inc.tmp" "${BUILD}/wn_mt_jump_tables.inc"
+fi
 ${NVCC} ${COMMON} ${PTXAS_V} -fmad=false -c "${HERE}/wn_tilegen.cu"        -o "${BUILD}/wn_tilegen.o"
 ${NVCC} ${COMMON} ${PTXAS_V} -fmad=false -c "${HERE}/wn_eval_exact.cu"     -o "${BUILD}/wn_eval_exact.o"
 ${NVCC} ${COMMON} ${PTXAS_V}             -c "${HERE}/wn_multiband_fast.cu" -o "${BUILD}/wn_multiband_fast.o"
