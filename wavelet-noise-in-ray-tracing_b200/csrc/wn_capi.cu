@@ -520,6 +520,7 @@ struct wn_tile {
     bool built = false;
     uint64_t version = 0;                // bumped whenever the coefficients change (on the compute stream)
     mutable uint64_t side_seen = ~0ull;  // version the side stream has been ordered after
+    mutable void *plan_cache = nullptr;  // host-side plan of the last fast lattice call on this tile (axes tables, fold decisions)
 };
 
 static WnTileView tile_view(const wn_tile *t)
@@ -573,6 +574,7 @@ extern "C" int wn_tile_destroy(wn_tile *t)
     cudaStreamSynchronize(t->ctx->side);
     cudaFree(t->d);
     cudaFree(t->dpad);
+    wn_mb3d_fast_cache_free(t->plan_cache);
     delete t;
     return WN_OK;
 }
@@ -910,6 +912,7 @@ extern "C" int wn_multiband3d_lattice(const wn_tile *t, const float *xs, int nx,
     static const int pdl_side_chain = [] { const char *e = getenv("WN_PDL_SIDE_CHAIN"); return e ? atoi(e) : 0; }();
     static const int pdl_side_main = [] { const char *e = getenv("WN_PDL_SIDE_MAIN"); return e ? atoi(e) : 0; }();
     plan.pdl = use_side ? pdl_side_chain : 1;
+    plan.axes_cache = &t->plan_cache;
     cudaStream_t chain = use_side ? c->side : c->stream;
     const int gen = (int)(c->side_calls & 1);
     if (use_side) {

@@ -97,6 +97,7 @@ struct WnFastPlan {
     int owns_tab;               // the top-level plan frees the tables
     int pdl;                    // launch this plan's kernels with programmatic dependent launch (set before prepare / run)
     void *host_axes;            // host copy of the tables (period detection, brick planning), shared by nested plans
+    void **axes_cache;          // set before prepare: the tile's plan-cache slot (nullptr: no caching across calls)
 };
 int  wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const float *h_ys, const float *h_zs, WnBands b,
                           WnFastPlan *plan, cudaStream_t st, int depth = 0);
@@ -104,6 +105,7 @@ int  wn_mb3d_fast_run(WnTileView t, WnLattice c, const float *h_ys, const float 
                       const unsigned char *all_rows, const WnFastPlan *plan, int k0, int nk, float *out, cudaStream_t st);
 void wn_mb3d_fast_finish(WnFastPlan *plan, cudaStream_t st);
 void wn_mb3d_fast_detach(WnFastPlan *plan, void **tab, void **P);
+void wn_mb3d_fast_cache_free(void *slot);      // releases a plan-cache slot (tile destruction)
 // host-only fold decision of the top level (diagnostics / CPU tests); returns the number of folded bands
 int  wn_mb3d_fast_plan_host(const float *h_xs, int nx, const float *h_ys, int ny, const float *h_zs, int nz, WnBands b,
                             int tile_n, int *folded, int block[3]);

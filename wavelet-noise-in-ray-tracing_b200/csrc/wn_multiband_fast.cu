@@ -1241,9 +1241,29 @@ struct HostEntry {
 
 static_assert(sizeof(HostEntry) == 16, "HostEntry is compared with memcmp");
 
+struct FoldDecision { int nfold; bool folded[WN_MAX_BANDS]; long long Lx, Ly, Lz; };
+
 struct HostAxes {
     int nb = 0, nx = 0, ny = 0, nz = 0;
     mutable int runs = 0;           // lattice kernels launched so far in this call (the first one follows k_axis_tables)
+    // Plan cache (one slot per tile object, see wn_mb3d_fast_prepare): a call whose axes, bands and tile edge are
+    // bitwise those of the previous call on the same tile reuses these host tables and the fold decisions made on them.
+    // Pure host-side planning -- every kernel of the call still runs.
+    bool cached = false;            // owned by a tile's cache slot, not by the call
+    int key_n = 0;
+    WnBands key_b;
+    std::vector<float> key_axes;    // xs | ys | zs
+    struct Memo { unsigned char rows[WN_MAX_BANDS]; int nbands, nx, ny, nz; long long budget; double level; FoldDecision fd; };
+    mutable std::vector<Memo> memo;
+    bool matches(const float *xs, int nx_, const float *ys, int ny_, const float *zs, int nz_, const WnBands &b, int n) const
+    {
+        if (nx_ != nx || ny_ != ny || nz_ != nz || n != key_n || b.nbands != nb) return false;
+        if (std::memcmp(b.scale, key_b.scale, sizeof(float) * b.nbands) != 0) return false;
+        if (key_axes.size() != (size_t)nx + ny + nz) return false;
+        return std::memcmp(key_axes.data(), xs, sizeof(float) * nx) == 0 &&
+               std::memcmp(key_axes.data() + nx, ys, sizeof(float) * ny) == 0 &&
+               std::memcmp(key_axes.data() + nx + ny, zs, sizeof(float) * nz) == 0;
+    }
     std::vector<HostEntry> e;       // [band][x | y | z]
     std::vector<int> first;         // unwrapped first tap cell, same layout
     size_t per_band() const { return (size_t)nx + ny + nz; }
@@ -1298,13 +1318,28 @@ HostAxes *acquire_host_axes()
 }
 void release_host_axes(HostAxes *h)
 {
-    if (!h) return;
+    if (!h || h->cached) return;
     if (!t_spare_axes) t_spare_axes = h; else delete h;
 }
 
-HostAxes *make_host_axes(const float *xs, int nx, const float *ys, int ny, const float *zs, int nz, const WnBands &b, int n)
+HostAxes *make_host_axes(const float *xs, int nx, const float *ys, int ny, const float *zs, int nz, const WnBands &b, int n,
+                         void **cache_slot = nullptr)
 {
-    HostAxes *h = acquire_host_axes();
+    static const bool cache_on = [] { const char *e = getenv("WN_PLAN_CACHE"); return !e || atoi(e) != 0; }();
+    HostAxes *h = nullptr;
+    if (cache_slot && cache_on) {
+        h = static_cast<HostAxes *>(*cache_slot);
+        if (h && h->matches(xs, nx, ys, ny, zs, nz, b, n)) { h->runs = 0; return h; }
+        if (!h) { h = new HostAxes; h->cached = true; *cache_slot = h; }
+        h->memo.clear();
+        h->key_n = n; h->key_b = b;
+        h->key_axes.resize((size_t)nx + ny + nz);
+        std::copy(xs, xs + nx, h->key_axes.begin());
+        std::copy(ys, ys + ny, h->key_axes.begin() + nx);
+        std::copy(zs, zs + nz, h->key_axes.begin() + nx + ny);
+    } else {
+        h = acquire_host_axes();
+    }
     h->runs = 0;
     h->nb = b.nbands; h->nx = nx; h->ny = ny; h->nz = nz;
     h->e.resize(h->per_band() * b.nbands);
@@ -1703,16 +1738,42 @@ long long lcm_capped(long long a, long long b, long long cap)
 }
 
 // ---- fold decision (pure host code; also behind wn_debug_fold_plan for the CPU tests) ------------------------------
-struct FoldDecision { int nfold; bool folded[WN_MAX_BANDS]; long long Lx, Ly, Lz; };
-
 // b: the bands of this (sub)lattice in canonical order, rows[i] = table row of band i; the lattice is the prefix
 // nx x ny x nz of the call's axes
+FoldDecision decide_fold_uncached(const HostAxes &hax, const unsigned char *rows, const WnBands &b, const float *h_xs,
+                                  const float *h_ys, const float *h_zs, int nx, int ny, int nz, long long budget,
+                                  double level_overhead);
+
+// the decision depends on the host tables, the band subset, the sub-lattice and the two tuning knobs: memoised on the
+// (cached) tables
 FoldDecision decide_fold(const HostAxes &hax, const unsigned char *rows, const WnBands &b, const float *h_xs,
                          const float *h_ys, const float *h_zs, int nx, int ny, int nz)
 {
-    const long long total = (long long)nx * ny * nz;
     long long budget = 1LL << 27;                              // samples in the period block: 512 MiB of scratch at most
     if (const char *e = getenv("WN_FOLD_BUDGET")) budget = atoll(e);
+    double level_overhead = 8e6;
+    if (const char *e = getenv("WN_FOLD_LEVEL_COST")) level_overhead = atof(e);   // tests fold tiny lattices with 0
+    if (hax.cached)
+        for (const HostAxes::Memo &m : hax.memo)
+            if (m.nbands == b.nbands && m.nx == nx && m.ny == ny && m.nz == nz && m.budget == budget && m.level == level_overhead &&
+                std::memcmp(m.rows, rows, b.nbands) == 0)
+                return m.fd;
+    const FoldDecision fd = decide_fold_uncached(hax, rows, b, h_xs, h_ys, h_zs, nx, ny, nz, budget, level_overhead);
+    if (hax.cached) {
+        HostAxes::Memo m;
+        std::memset(&m, 0, sizeof(m));
+        std::memcpy(m.rows, rows, b.nbands);
+        m.nbands = b.nbands; m.nx = nx; m.ny = ny; m.nz = nz; m.budget = budget; m.level = level_overhead; m.fd = fd;
+        hax.memo.push_back(m);
+    }
+    return fd;
+}
+
+FoldDecision decide_fold_uncached(const HostAxes &hax, const unsigned char *rows, const WnBands &b, const float *h_xs,
+                                  const float *h_ys, const float *h_zs, int nx, int ny, int nz, long long budget,
+                                  double level_overhead)
+{
+    const long long total = (long long)nx * ny * nz;
     struct Cand { int band; int px, py, pz; long long vol; };
     std::vector<Cand> cand;
     // relative per-sample cost of evaluating a band directly, from its step in tile cells per sample (fitted to the
@@ -1753,8 +1814,6 @@ FoldDecision decide_fold(const HostAxes &hax, const unsigned char *rows, const W
     // enlarges the fold to, plus the add of the previous level:
     //   cost = (sum_direct c_b + 0.3) * total + sum_{i folded} ((c_i + 0.3) * block_i + level)
     // in units of one band-sample (~1 ps of GPU time); level = the latency of one more small dependent launch (~8 us).
-    double level_overhead = 8e6;
-    if (const char *e = getenv("WN_FOLD_LEVEL_COST")) level_overhead = atof(e);   // tests fold tiny lattices with 0
     // Per-sample cost of the bands left direct when the first nd canonical bands (lowest scales) stay direct:
     // the sum of their costs plus 0.3 for adding the period-block value.  The replica kernel changes that for one or two
     // direct bands on a lattice whose halves are replicas: the period-block value (and a coinciding higher band) is
@@ -1870,7 +1929,8 @@ int wn_mb3d_fast_prepare(WnTileView t, WnLattice c, const float *h_xs, const flo
         plan->tab_bands = b.nbands; plan->sx = nx; plan->sy = ny; plan->sz = nz;
         for (int i = 0; i < WN_MAX_BANDS; ++i) plan->direct_rows[i] = (unsigned char)i;
         plan->owns_tab = 1;
-        plan->host_axes = make_host_axes(h_xs, std::max(nx, 0), h_ys, std::max(ny, 0), h_zs, std::max(nz, 0), b, t.n);
+        plan->host_axes = make_host_axes(h_xs, std::max(nx, 0), h_ys, std::max(ny, 0), h_zs, std::max(nz, 0), b, t.n,
+                                         plan->axes_cache);
         if (nx <= 0 || ny <= 0 || nz <= 0 || b.nbands <= 0) return 0;
         const size_t per_band = (size_t)nx + ny + nz;
         if (wn_scratch_alloc((void **)&plan->tab, per_band * b.nbands * sizeof(float4), st) != cudaSuccess) return -1;
@@ -1971,6 +2031,8 @@ int wn_mb3d_fast_plan_host(const float *h_xs, int nx, const float *h_ys, int ny,
     }
     return fd.nfold;
 }
+
+void wn_mb3d_fast_cache_free(void *slot) { delete static_cast<HostAxes *>(slot); }
 
 void wn_mb3d_fast_finish(WnFastPlan *plan, cudaStream_t st)
 {
