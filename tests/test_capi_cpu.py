@@ -146,6 +146,35 @@ def test_viewer_json_format_matches_reference_converter(golden_dir):
     assert got["data"] == want["data"]
 
 
+def test_export_json_writes_the_viewer_files(golden_dir, tmp_path):
+    """export_json on the 15 shipped images: the reference viewer's file names (threejs/result_json/*.json) and, when the
+    reference tree is present, the same JSON content as threejs/convert_raw_to_json.py produced."""
+    import json
+    import numpy as np
+    import experiment_cases as ex
+    exp = wnpkg.load_sub("experiment")
+    images = {}
+    for octave in ex.OCTAVES:
+        for kind in ("w2d", "w3d", "wproj", "p2d", "p3d"):
+            images[ex.raw_name(kind, octave)[:-4]] = ex.load_raw(golden_dir, kind, octave)
+    exp.export_json(images, str(tmp_path))
+    names = sorted(os.listdir(tmp_path))
+    assert len(names) == 15 and "wavelet_noise_3d_projected_octave5.json" in names and "perlin_noise_2d_octave3.json" in names
+    ref_dir = "/root/reference/threejs/result_json"
+    for name in names:
+        got = json.load(open(tmp_path / name))
+        assert got["width"] == 256 and got["height"] == 256 and len(got["data"]) == 65536
+        assert 0.0 <= min(got["data"]) and max(got["data"]) <= 1.0
+        if os.path.isdir(ref_dir):
+            want = json.load(open(os.path.join(ref_dir, name)))
+            # min / max (and the data normalised with them) exactly; mean / std to the last-digit differences between
+            # numpy versions (the shipped files were written by another one)
+            g, w = got["original_range"], want["original_range"]
+            assert g["min"] == w["min"] and g["max"] == w["max"], name
+            assert abs(g["mean"] - w["mean"]) <= 1e-12 and abs(g["std"] - w["std"]) <= 1e-12, name
+            assert got["data"] == want["data"], name
+
+
 def test_bench_helpers():
     import importlib.util
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))

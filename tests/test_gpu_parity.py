@@ -122,6 +122,38 @@ def test_odd_offset_flag_matches_paper_restatement(wn, oracle):
     assert_bits(w.getNoiseCoefficients(), want, "odd-offset tile")
 
 
+def test_tile_cache_round_trip(wn, oracle, tmp_path):
+    """Tile cache: a miss generates on the GPU and writes the file, a hit uploads it; both objects hold the oracle's
+    tile bit for bit and continue the generator stream identically (the second tile of each equals the oracle's)."""
+    g = oracle.rng(4242)
+    want1 = oracle.generate_tile(32, 4242, 3, g)
+    want2 = oracle.generate_tile(32, 4242, 3, g)
+    a = wn.WaveletNoise(32, 4242)
+    assert a.generate_cached(3, str(tmp_path)) is False
+    b = wn.WaveletNoise(32, 4242)
+    assert b.generate_cached(3, str(tmp_path)) is True
+    for w in (a, b):
+        assert_bits(w.getNoiseCoefficients(), want1, "cached tile")
+        w.generateNoiseTile3D()
+        assert_bits(w.getNoiseCoefficients(), want2, "tile after the cached one")
+    with pytest.raises(wn.WnError):
+        b.generate_cached(3, str(tmp_path))
+
+
+def test_gpu_stats_match_the_viewer_json_ranges(wn, golden_dir):
+    """The viewer JSON's original_range (threejs/convert_raw_to_json.py:46-49: float64 min / max / mean / std of the
+    float32 image) against wn_stats_compute on the 15 shipped images: min and max exactly, mean and variance to float32
+    rounding (calculateStats accumulates in double and narrows to float, WaveletNoise.cpp:268-288)."""
+    ctx = wn.default_context()
+    for octave in ex.OCTAVES:
+        for kind in ("w2d", "w3d", "wproj", "p2d", "p3d"):
+            img = ex.load_raw(golden_dir, kind, octave).ravel()
+            st = ctx.stats(img)
+            a = img.astype(np.float64)
+            assert st.min_val == np.float32(a.min()) and st.max_val == np.float32(a.max())
+            assert abs(st.avg - a.mean()) <= 1e-6 and abs(st.var - a.std() ** 2) <= 2e-6 * max(1.0, a.std() ** 2)
+
+
 def test_stats(wn, oracle, gpu_tiles, tiles128):
     st = gpu_tiles[3].ctx.stats(tiles128[3])
     avg, var, mn, mx = oracle.stats(tiles128[3])

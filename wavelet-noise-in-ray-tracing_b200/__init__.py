@@ -306,6 +306,41 @@ class WaveletNoise:
         self._new_tile(dims)
         check(lib.wn_tile_build_seeded(self._tile, self.randomSeed if seed is None else int(seed), None))
 
+    # ---- tile cache (SURVEY.md section 5 "checkpoint / resume": the tile is a pure function of n, dims, seed, flags) ----
+    def cache_path(self, dims, cache_dir):
+        import os
+        return os.path.join(cache_dir, f"wn_tile_n{self.tileSizeN}_d{dims}_seed{self.randomSeed}_f{self.flags}.raw")
+
+    def generate_cached(self, dims, cache_dir):
+        """First tile of a fresh object through a file cache: float32 little-endian `.raw` in memory order (the format
+        experient/analyze.py:6-21 reads), named after (n, dims, seed, flags).  A hit uploads the coefficients and
+        advances the host generator past the fill it skipped -- the object is indistinguishable from one that generated
+        the tile; a miss generates on the GPU and writes the file.  Returns True on a hit."""
+        import os
+        if not self._fresh:
+            raise WnError(-5, "generate_cached: the generator of this object has already been used")
+        path = self.cache_path(dims, cache_dir)
+        count = self.tileSizeN ** dims
+        if os.path.exists(path) and os.path.getsize(path) == 4 * count + 8:
+            blob = np.fromfile(path, dtype="<u1")
+            draws = int(blob[-8:].view("<u8")[0])
+            self.upload(blob[:-8].view("<f4"), dims)
+            check(lib.wn_rng_discard(self._rng, draws))
+            self._fresh = False
+            return True
+        self._new_tile(dims)
+        draws = C.c_ulonglong(0)
+        check(lib.wn_tile_build_seeded(self._tile, self.randomSeed, C.byref(draws)))
+        check(lib.wn_rng_discard(self._rng, draws.value))
+        self._fresh = False
+        os.makedirs(cache_dir, exist_ok=True)
+        tmp = path + f".tmp{os.getpid()}"
+        with open(tmp, "wb") as f:                      # coefficients, then the raw draws the fill consumed (uint64)
+            f.write(np.ascontiguousarray(self.getNoiseCoefficients(), "<f4").tobytes())
+            f.write(np.array([draws.value], "<u8").tobytes())
+        os.replace(tmp, path)
+        return False
+
     def upload(self, coefficients, dims):
         """Adopt finished coefficients (n^dims floats)."""
         self._new_tile(dims)
