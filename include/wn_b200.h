@@ -166,6 +166,17 @@ int  wn_multiband3d_points(const wn_tile *tile, const float *p, size_t count,
                            const float *band_scale, const float *weights, int nbands,
                            float post_scale, float *out, int space);
 
+/* The paper's own multiband entry point (Cook & DeRose 2005, Appendix 2), which the reference omits (it only ever
+ * evaluates one band):  WMultibandNoise(p, s, normal, firstBand, nbands, w) =
+ *   sum over b < nbands while s + firstBand + b < 0 of w[b] * (normal ? WProjectedNoise(q, normal) : WNoise(q)),
+ *   q = 2 p 2^(firstBand+b), divided by sqrt(sum_b w[b]^2 * (normal ? 0.296 : 0.210)) over ALL nbands weights.
+ * s is the scale cut-off (log2 of the sample footprint: bands finer than the footprint are dropped), normal is NULL or
+ * three floats shared by the batch (HOST pointer).  WNoise / WProjectedNoise are the reference's evaluate3D /
+ * evaluate3DProjected (WaveletNoise.cpp:185-265).  Note the paper's variance constant 0.210 where the reference's
+ * drivers use 0.18402 (experient/main.cpp:43). */
+int  wn_wmultiband_points(const wn_tile *tile, const float *p, size_t count, float s, const float *normal,
+                          int first_band, int nbands, const float *w, float *out, int space);
+
 /* ---- evaluation: lattices (axis-aligned grids given by coordinate arrays) -------------------
  * sample (i,j,k) = (xs[i], ys[j], zs[k]); the caller computes the axes with whatever float formula
  * it uses (the reference: u = (float(x)/size)*4.0f, experient/main.cpp:20-21), so coordinates are

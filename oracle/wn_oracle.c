@@ -502,6 +502,36 @@ void orc_multiband3d_points(const float *N, int n, const float *p, size_t count,
         out[i] = orc_multiband_at(N, n, p[3 * i], p[3 * i + 1], p[3 * i + 2], bs, w, nb) * post;
 }
 
+/* Cook & DeRose 2005, Appendix 2, WMultibandNoise(p, s, normal, firstBand, nbands, w) restated statement by statement
+ * over the reference's evaluate3D / evaluate3DProjected (the reference itself has no multiband function):
+ *   for (b = 0; b < nbands && s + firstBand + b < 0; b++) { q = 2 p 2^(firstBand+b); result += w[b] * (normal ?
+ *       WProjectedNoise(q, normal) : WNoise(q)); }
+ *   variance = sum over ALL nbands of w[b]^2;  if (variance) result /= sqrt(variance * (normal ? 0.296 : 0.210));
+ * PARITY UNPINNED: no reference code or artefact exists for this composition; pow() is exact for integer exponents. */
+float orc_wmultiband(const float *N, int n, const float p[3], float s, const float *normal, int first_band, int nbands,
+                     const float *w)
+{
+    float q[3], result = 0, variance = 0;
+    int i, b;
+    for (b = 0; b < nbands && s + first_band + b < 0; b++) {
+        for (i = 0; i <= 2; i++) q[i] = (float)(2 * p[i] * pow(2, first_band + b));
+        result += normal ? w[b] * orc_eval3d_projected(N, n, q, normal) : w[b] * orc_eval3d(N, n, q);
+    }
+    for (b = 0; b < nbands; b++) variance += w[b] * w[b];
+    if (variance) result = (float)(result / sqrt(variance * (normal ? 0.296 : 0.210)));
+    return result;
+}
+
+void orc_wmultiband_points(const float *N, int n, const float *p, size_t count, float s, const float *normal,
+                           int first_band, int nbands, const float *w, float *out, int threads)
+{
+    int nt = orc_threads(threads); (void)nt;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nt) schedule(static)
+#endif
+    for (long long i = 0; i < (long long)count; ++i) out[i] = orc_wmultiband(N, n, p + 3 * i, s, normal, first_band, nbands, w);
+}
+
 /* experient/main.cpp:18-30 */
 void orc_eval2d_lattice(const float *N, int n, const float *xs, int nx, const float *ys, int ny,
                         float pre, float post, float *out, int threads)

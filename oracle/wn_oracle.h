@@ -89,6 +89,11 @@ void orc_multiband3d_lattice(const float *N, int n,
                              const float *zs, int nz,
                              const float *band_scale, const float *weights, int nbands,
                              float post_scale, float *out, int threads);
+/* paper Appendix 2 WMultibandNoise (s = scale cut-off, normal NULL -> WNoise); parity unpinned */
+float orc_wmultiband(const float *N, int n, const float p[3], float s, const float *normal, int first_band, int nbands,
+                     const float *w);
+void orc_wmultiband_points(const float *N, int n, const float *p_aos, size_t count, float s, const float *normal,
+                           int first_band, int nbands, const float *w, float *out, int threads);
 void orc_multiband3d_points(const float *N, int n, const float *p_aos, size_t count,
                             const float *band_scale, const float *weights, int nbands,
                             float post_scale, float *out, int threads);

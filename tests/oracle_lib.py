@@ -169,6 +169,18 @@ class Oracle:
                                        _fp(bs), _fp(w), bs.size, post, _fp(out), threads)
         return out
 
+    def wmultiband_points(self, N, n, pts, s, normal, first_band, weights, threads=0):
+        """Paper App. 2 WMultibandNoise(p, s, normal, firstBand, nbands, w) per point (normal None -> WNoise)."""
+        N, pts, w = _f32(N), _f32(pts).reshape(-1, 3), _f32(weights)
+        out = np.empty(pts.shape[0], np.float32)
+        nv = None if normal is None else _f32(normal)
+        self.L.orc_wmultiband_points.argtypes = [f32p, C.c_int, f32p, C.c_size_t, C.c_float, f32p, C.c_int, C.c_int, f32p,
+                                                 f32p, C.c_int]
+        self.L.orc_wmultiband_points.restype = None
+        self.L.orc_wmultiband_points(_fp(N), n, _fp(pts), out.size, float(s), None if nv is None else _fp(nv),
+                                     int(first_band), w.size, _fp(w), _fp(out), threads)
+        return out
+
     def multiband3d_points(self, N, n, pts, band_scale, weights, post=1.0, threads=0):
         pts, bs, w = map(_f32, (pts, band_scale, weights))
         out = np.empty(pts.size // 3, np.float32)

@@ -441,6 +441,44 @@ def test_axis_table_tap_cells_are_the_reference_integers(wn, oracle, gpu_tiles):
                 assert list(idx) == mine, (p, n)
 
 
+def test_band_limits_by_power_spectrum(wn):
+    """What experient/analyze.py:398-527 shows as pictures (the paper's Figures 8 and 9), asserted as numbers from a GPU
+    FFT on freshly generated 512^2 octave-4 images: 2D wavelet noise is band-limited (>= 93 % of its power inside the
+    band, < 0.3 % below half its lower edge); a 2D slice of 3D noise leaks low frequencies (> 3 %); projecting along the
+    normal restores the band limit (< 1 %); Perlin noise is not band-limited (> 2 %)."""
+    expm = wnpkg.load_sub("experiment")
+    n2, n3, pn = wn.WaveletNoise(128, 12345), wn.WaveletNoise(128, 12345), wn.PerlinNoise(12345)
+    n2.generateNoiseTile2D()
+    n3.generateNoiseTile3D()
+    size, octave = 512, 4
+    cells_per_pixel = 4.0 / size * 2.0 ** octave * 2.0         # u = x/size*4, q = 2 u 2^octave
+    in2, lo2 = expm.band_energy(expm.generate2DOctaveBandNoise(size, octave, None, n2), cells_per_pixel)
+    in3, lo3 = expm.band_energy(expm.generate3DSlicedOctaveBandNoise(size, octave, None, n3), cells_per_pixel)
+    inp, lop = expm.band_energy(expm.generate3DProjectedOctaveBandNoise(size, octave, None, n3), cells_per_pixel)
+    _, lperlin = expm.band_energy(expm.generatePerlinNoise2D(size, octave, None, pn), cells_per_pixel / 2.0)
+    assert in2 >= 0.93 and lo2 <= 0.003, (in2, lo2)
+    assert lo3 >= 0.03, lo3
+    assert inp >= 0.90 and lop <= 0.01, (inp, lop)
+    assert lperlin >= 0.02, lperlin
+
+
+def test_paper_wmultibandnoise_signature(wn, oracle, gpu_tiles, tiles128):
+    """Cook & DeRose App. 2 WMultibandNoise(p, s, normal, firstBand, nbands, w): band cut-off by the scale s, optional
+    projection normal, variance normalisation over all nbands weights -- BIT-EXACT against the statement-by-statement
+    restatement over the oracle's evaluate3D / evaluate3DProjected (parity unpinned by the reference: it has no
+    multiband function)."""
+    t = gpu_tiles[3]
+    rs = np.random.RandomState(31)
+    pts = np.concatenate([rs.uniform(-3, 3, (3000, 3)), rs.uniform(-200, 200, (1000, 3))]).astype(np.float32)
+    w = np.array([1.0, 0.5, 0.25, 0.125, 0.0625], np.float32)
+    nrm = (np.array([1, 2, 3], np.float64) / np.sqrt(14.0)).astype(np.float32)
+    for s, first, normal in ((-20.0, -2, None), (-3.5, -6, None), (-1.0, -3, nrm), (-20.0, 0, nrm), (5.0, -2, None)):
+        got = t.WMultibandNoise(pts, s, normal, first, w)
+        want = oracle.wmultiband_points(tiles128[3], 128, pts, s, normal, first, w)
+        assert_bits(got, want, f"WMultibandNoise s={s} first={first} normal={normal is not None}")
+    assert not t.WMultibandNoise(pts, 5.0, None, -2, w).any()          # every band cut off
+
+
 def test_large_host_call_is_chunked_consistently(wn, gpu_tiles):
     """A WN_HOST lattice larger than one staging chunk equals the same lattice computed in one device call."""
     t = gpu_tiles[3]

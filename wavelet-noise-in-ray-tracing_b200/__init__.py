@@ -454,6 +454,20 @@ class WaveletNoise:
                                         C.c_void_p(w.ctypes.data), bs.size, post_scale, C.c_void_p(optr), space))
         return out
 
+    def WMultibandNoise(self, pts, s, normal, firstBand, w, out=None):
+        """Cook & DeRose App. 2 WMultibandNoise(p, s, normal, firstBand, nbands, w) for a batch of points (normal None or
+        three floats shared by the batch; nbands = len(w))."""
+        self._need()
+        ptr, space, keep = _in(pts)
+        count = (keep.numel() if _is_torch(keep) else keep.size) // 3
+        optr, out = _out(out, (count,), space, keep if _is_torch(keep) else None)
+        w = _host(w)
+        nv = None if normal is None else _host(normal)
+        check(lib.wn_wmultiband_points(self._tile, C.c_void_p(ptr), count, float(s),
+                                       None if nv is None else C.c_void_p(nv.ctypes.data), int(firstBand), w.size,
+                                       C.c_void_p(w.ctypes.data), C.c_void_p(optr), space))
+        return out
+
     def evaluate2D_lattice(self, xs, ys, pre_scale=1.0, post_scale=1.0, out=None, device_out=False):
         self._need()
         xs, ys = _host(xs), _host(ys)

@@ -69,6 +69,7 @@ SIGNATURES = {
     "wn_eval3d_points": (C.c_int, [vp, vp, C.c_size_t, C.c_float, C.c_float, vp, C.c_int]),
     "wn_eval3d_projected_points": (C.c_int, [vp, vp, vp, C.c_int, C.c_size_t, C.c_float, C.c_float, vp, C.c_int]),
     "wn_multiband3d_points": (C.c_int, [vp, vp, C.c_size_t, vp, vp, C.c_int, C.c_float, vp, C.c_int]),
+    "wn_wmultiband_points": (C.c_int, [vp, vp, C.c_size_t, C.c_float, vp, C.c_int, C.c_int, vp, vp, C.c_int]),
     "wn_eval2d_lattice": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_float, C.c_float, vp, C.c_int]),
     "wn_multiband3d_lattice": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_float,
                                          C.c_int, vp, C.c_int]),

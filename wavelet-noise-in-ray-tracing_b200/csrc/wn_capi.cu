@@ -792,6 +792,39 @@ extern "C" int wn_multiband3d_points(const wn_tile *t, const float *p, size_t co
     });
 }
 
+// Cook & DeRose App. 2: WMultibandNoise(p, s, normal, firstBand, nbands, w)
+extern "C" int wn_wmultiband_points(const wn_tile *t, const float *p, size_t count, float s, const float *normal,
+                                    int first_band, int nbands, const float *w, float *out, int space)
+{
+    WN_NEED_TILE(t, 3, "wn_wmultiband_points");
+    WN_NEED_SPACE(space);
+    WN_REQUIRE(nbands >= 1 && nbands <= WN_MAX_BANDS && w, "wn_wmultiband_points: nbands must be in [1,%d] and w not NULL", WN_MAX_BANDS);
+    WN_REQUIRE(first_band > -60 && first_band + nbands < 60, "wn_wmultiband_points: band range out of range");
+    if (!count) return WN_OK;
+    WN_REQUIRE(p && out, "wn_wmultiband_points: NULL buffer");
+    WnBands b;
+    std::memset(&b, 0, sizeof(b));
+    b.nbands = nbands; b.post = 1.0f;
+    float variance = 0.0f;
+    int active = 0;
+    for (int k = 0; k < nbands; ++k) {
+        b.scale[k] = (float)std::pow(2.0, first_band + k);
+        b.weight[k] = w[k];
+        variance += w[k] * w[k];
+        if (active == k && s + first_band + k < 0) ++active;       // the listing's loop stops at the first band cut off
+    }
+    const double denom = variance ? std::sqrt(variance * (normal ? 0.296 : 0.210)) : 0.0;
+    wn_ctx *c = t->ctx;
+    DeviceGuard g(c->device);
+    const WnTileView tv = tile_view(t);
+    if (space == WN_DEVICE)
+        return run_device(c, [&](cudaStream_t st) { return wn_launch_wmultiband(tv, p, count, b, active, normal, denom, out, st); });
+    ChunkIO io; io.in = p; io.in_item = 3 * sizeof(float); io.out = out;
+    return run_chunked_host(c, count, kChunkSamples / 4, io, [&](void *din, void *, float *dout, size_t, size_t cnt, cudaStream_t st) {
+        return wn_launch_wmultiband(tv, (const float *)din, cnt, b, active, normal, denom, dout, st);
+    });
+}
+
 // evaluate3D(p*pre)*post == multiband with one band {scale=pre, weight=1}: 0 + 1*v == v and v*post, bit-exact
 extern "C" int wn_eval3d_points(const wn_tile *t, const float *p, size_t count, float pre, float post, float *out, int space)
 {

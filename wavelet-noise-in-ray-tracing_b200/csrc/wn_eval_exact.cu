@@ -314,6 +314,25 @@ __global__ void k_proj(WnTileView t, C c, const float *normals, float n0, float 
     if (normals) { nrm[0] = __ldg(normals + 3 * s); nrm[1] = __ldg(normals + 3 * s + 1); nrm[2] = __ldg(normals + 3 * s + 2); }
     out[s] = FMUL(eval3d_projected(t, p, nrm), post);
 }
+// Cook & DeRose App. 2 WMultibandNoise(p, s, normal, firstBand, nbands, w), statement by statement: active bands b < nb_active (s + firstBand + b < 0, decided on the host), q = 2 p
+// 2^(firstBand+b) evaluated in double like the listing's pow(), result /= sqrt(variance * (normal ? 0.296 : 0.210)).
+__global__ void k_wmultiband(WnTileView t, const float *p, size_t count, WnBands b /* scale[] = 2^(firstBand+b) */,
+                             int nb_active, int projected, float n0, float n1, float n2, double denom, float *out)
+{
+    WN_TID_OR_RETURN(count);
+    const float nrm[3] = { n0, n1, n2 };
+    float result = 0.0f;
+    for (int k = 0; k < nb_active; ++k) {
+        float q[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) q[i] = (float)__dmul_rn(__dmul_rn(2.0, (double)__ldg(p + 3 * s + i)), (double)b.scale[k]);
+        const float v = projected ? eval3d_projected(t, q, nrm) : eval3d(t, q[0], q[1], q[2]);
+        result = FADD(result, FMUL(b.weight[k], v));
+    }
+    if (denom != 0.0) result = (float)__ddiv_rn((double)result, denom);
+    out[s] = result;
+}
+
 template <class C, bool FAST>
 __global__ void k_perlin(const int32_t *perm, C c, size_t first, size_t count, float *out)
 {
@@ -482,6 +501,14 @@ int wn_launch_perlin_affine(const int32_t *perm, WnAffine c, size_t first, size_
     if (!count) return 0;
     if (fast) k_perlin<WnAffine, true><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
     else k_perlin<WnAffine, false><<<blocks_for(count, WN_T), WN_T, 0, st>>>(perm, c, first, count, out);
+    return 1;
+}
+int wn_launch_wmultiband(WnTileView t, const float *p, size_t count, WnBands b, int nb_active, const float *normal,
+                         double denom, float *out, cudaStream_t st)
+{
+    if (!count) return 0;
+    k_wmultiband<<<blocks_for(count, 128), 128, 0, st>>>(t, p, count, b, nb_active, normal != nullptr, normal ? normal[0] : 0.0f,
+                                                         normal ? normal[1] : 0.0f, normal ? normal[2] : 0.0f, denom, out);
     return 1;
 }
 int wn_launch_perlin_points_f64(const int32_t *perm, const double *p, size_t count, double *out, cudaStream_t st)

@@ -70,6 +70,9 @@ int wn_launch_proj_affine(WnTileView t, WnAffine c, const float nrm[3], size_t f
 int wn_launch_perlin_points(const int32_t *perm, WnPointsAoS c, size_t first, size_t count, float *out, int fast, cudaStream_t st);
 int wn_launch_perlin_lattice(const int32_t *perm, WnLattice c, size_t first, size_t count, float *out, int fast, cudaStream_t st);
 int wn_launch_perlin_affine(const int32_t *perm, WnAffine c, size_t first, size_t count, float *out, int fast, cudaStream_t st);
+// paper App. 2 WMultibandNoise on points: b.scale[k] = 2^(firstBand+k), b.weight[k] = w[k]; normal = host pointer or nullptr
+int wn_launch_wmultiband(WnTileView t, const float *p, size_t count, WnBands b, int nb_active, const float *normal,
+                         double denom, float *out, cudaStream_t st);
 int wn_launch_perlin_points_f64(const int32_t *perm, const double *p, size_t count, double *out, cudaStream_t st);
 // texture hooks: scale (double) and octave as in texture.h
 int wn_launch_wavelet_texture(WnTileView t, const float *p, size_t count, double scale, float oct2, float inv_std,

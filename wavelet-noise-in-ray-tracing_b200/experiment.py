@@ -91,6 +91,35 @@ def generatePerlinNoise3DSliced(imageSize, octave, outputFile, perlin):
     return image
 
 
+def radial_power_spectrum(image):
+    """Radially averaged power spectrum of a square image, computed on the GPU (torch.fft = cuFFT): mean removed,
+    |fftshift(fft2)|^2 summed over integer-radius rings.  Same quantity as experient/analyze.py:81-157 plots (its
+    `power_spectrum` / radial profile), returned as a float64 numpy array indexed by ring radius in FFT bins."""
+    import torch
+    a = torch.as_tensor(np.ascontiguousarray(image, np.float32), device="cuda").double()
+    n = a.shape[0]
+    a = a - a.mean()
+    power = torch.fft.fftshift(torch.fft.fft2(a)).abs() ** 2
+    yy, xx = torch.meshgrid(torch.arange(n, device="cuda"), torch.arange(n, device="cuda"), indexing="ij")
+    ring = torch.sqrt(((xx - n // 2) ** 2 + (yy - n // 2) ** 2).double()).long()
+    prof = torch.zeros(int(ring.max()) + 1, dtype=torch.float64, device="cuda")
+    prof.scatter_add_(0, ring.flatten(), power.flatten())
+    return prof.cpu().numpy()
+
+
+def band_energy(image, cells_per_pixel):
+    """Where the power of a single-band noise image lies relative to the band the wavelet construction promises, [1/4, 1/2]
+    cycles per tile cell (Cook & DeRose section 3; the paper's Figure 8 / analyze.py:398-463 judge this by eye):
+    returns (fraction inside the band widened by 20 % / 15 %, fraction below half the band's lower edge)."""
+    prof = radial_power_spectrum(image)
+    n = np.asarray(image).shape[0]
+    lo, hi = n * 0.25 * cells_per_pixel, n * 0.5 * cells_per_pixel
+    total = prof[1:].sum()
+    inband = prof[max(1, int(lo * 0.8)):int(hi * 1.15) + 1].sum()
+    below = prof[1:max(1, int(lo * 0.5))].sum()
+    return float(inband / total), float(below / total)
+
+
 def raw_to_json_dict(image):
     """The JSON the reference's viewer loads (threejs/convert_raw_to_json.py:12-90): width, height,
     original_range{min,max,mean,std} (float64 statistics of the float32 image) and the data normalised to [0,1]."""
