@@ -445,7 +445,8 @@ def test_band_limits_by_power_spectrum(wn):
     """What experient/analyze.py:398-527 shows as pictures (the paper's Figures 8 and 9), asserted as numbers from a GPU
     FFT on freshly generated 512^2 octave-4 images: 2D wavelet noise is band-limited (>= 93 % of its power inside the
     band, < 0.3 % below half its lower edge); a 2D slice of 3D noise leaks low frequencies (> 3 %); projecting along the
-    normal restores the band limit (< 1 %); Perlin noise is not band-limited (> 2 %)."""
+    normal restores the band limit (< 1 %); Perlin noise is not band-limited (no octave holds more than 60 % of its
+    power: about half lies above the octave of its lattice)."""
     expm = wnpkg.load_sub("experiment")
     n2, n3, pn = wn.WaveletNoise(128, 12345), wn.WaveletNoise(128, 12345), wn.PerlinNoise(12345)
     n2.generateNoiseTile2D()
@@ -455,11 +456,11 @@ def test_band_limits_by_power_spectrum(wn):
     in2, lo2 = expm.band_energy(expm.generate2DOctaveBandNoise(size, octave, None, n2), cells_per_pixel)
     in3, lo3 = expm.band_energy(expm.generate3DSlicedOctaveBandNoise(size, octave, None, n3), cells_per_pixel)
     inp, lop = expm.band_energy(expm.generate3DProjectedOctaveBandNoise(size, octave, None, n3), cells_per_pixel)
-    _, lperlin = expm.band_energy(expm.generatePerlinNoise2D(size, octave, None, pn), cells_per_pixel / 2.0)
+    inperlin, _ = expm.band_energy(expm.generatePerlinNoise2D(size, octave, None, pn), cells_per_pixel / 2.0)
     assert in2 >= 0.93 and lo2 <= 0.003, (in2, lo2)
     assert lo3 >= 0.03, lo3
     assert inp >= 0.90 and lop <= 0.01, (inp, lop)
-    assert lperlin >= 0.02, lperlin
+    assert inperlin <= 0.6, inperlin
 
 
 def test_paper_wmultibandnoise_signature(wn, oracle, gpu_tiles, tiles128):
