@@ -16,8 +16,6 @@
 // The tile (8 MiB at n = 128) stays L2-resident; taps are read through the read-only path.
 #include "wn_internal.h"
 
-#include <cstdlib>
-
 namespace {
 
 #define FMUL __fmul_rn
@@ -194,111 +192,6 @@ __device__ float eval3d_projected(const WnTileView &t, const float p[3], const f
     return result;
 }
 
-// Warp-uniform form for coherent batches (image grids: the lanes of a warp are neighbouring pixels, a fraction of a tile
-// cell apart).  eval3d_projected() lets every lane walk its own bounding box and its own admissible x interval per row;
-// the trip counts differ from lane to lane, and a warp executes the union of all of them with most lanes idle (ncu: 25
-// of 32 lanes active, ~55 instructions per candidate slot).  Here the three loops run over the UNION of the lanes' boxes
-// and row intervals (warp min / max reductions, one redux instruction each), so the control flow is the same for every
-// lane and each candidate cell is evaluated by all lanes at once.  A lane may now evaluate candidates outside its own
-// conservative interval -- those get weight 0 from the reference's own tests and contribute nothing -- and it still
-// meets its contributing candidates in the reference's order (z outer, x inner) with the reference's arithmetic, so the
-// result is bit-identical to eval3d_projected().  All 32 lanes must call this (inactive lanes pass live = false).
-__device__ float eval3d_projected_warp(const WnTileView &t, const float p[3], const float nrm[3], bool live)
-{
-    int lo[3], hi[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const float support = FADD(FMUL(3.0f, fabsf(nrm[i])),
-                                   FMUL(3.0f, __fsqrt_rn(FMUL(FSUB(1.0f, FMUL(nrm[i], nrm[i])), 0.5f))));
-        lo[i] = (int)ceilf(FSUB(p[i], support));
-        hi[i] = (int)floorf(FADD(p[i], support));
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-        if (hi[i] - lo[i] > 12 || hi[i] < lo[i] - 1 || hi[i] == 0x7fffffff) live = false;     // see eval3d_projected
-    const unsigned full = 0xffffffffu;
-    int ulo[3], uhi[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        ulo[i] = __reduce_min_sync(full, live ? lo[i] : 0x7fffffff);
-        uhi[i] = __reduce_max_sync(full, live ? hi[i] : (int)0x80000000);
-    }
-    if (ulo[0] > uhi[0]) return 0.0f;                          // no live lane
-    // a warp whose lanes are far apart (not an image grid after all) would walk a huge union: each lane on its own then
-    if ((long long)(uhi[0] - ulo[0]) + (uhi[1] - ulo[1]) + (uhi[2] - ulo[2]) > 48) return live ? eval3d_projected(t, p, nrm) : 0.0f;
-    const float q0 = FSUB(p[0], 1.5f), q1 = FSUB(p[1], 1.5f), q2 = FSUB(p[2], 1.5f);
-    const float pmax = fmaxf(fmaxf(fabsf(p[0]), fabsf(p[1])), fabsf(p[2])) + 16.0f;
-    const float eps = pmax * 9.6e-7f + 1e-4f;
-    const float b0 = 1.0f - 0.5f * nrm[0] * nrm[0];
-    const float b1 = 0.5f * nrm[0] * nrm[1];
-    const float b2 = 0.5f * nrm[0] * nrm[2];
-    const bool use1 = fabsf(b1) > 1e-6f, use2 = fabsf(b2) > 1e-6f;
-    const float ib0 = 1.0f / b0, ib1 = use1 ? 1.0f / b1 : 0.0f, ib2 = use2 ? 1.0f / b2 : 0.0f;
-    float result = 0.0f;
-    for (int c2 = ulo[2]; c2 <= uhi[2]; ++c2) {
-        const float f2 = (float)c2;
-        const int i2 = tmod(c2, t) * t.n * t.n;
-        const float D2 = p[2] - f2;
-        const float d2n = FMUL(nrm[2], FSUB(p[2], f2));
-        for (int c1 = ulo[1]; c1 <= uhi[1]; ++c1) {
-            const float f1 = (float)c1;
-            const int i1 = tmod(c1, t) * t.n;
-            const float D1 = p[1] - f1;
-            const float K = nrm[1] * D1 + nrm[2] * D2;
-            float dlo = -1e30f, dhi = 1e30f;
-            {
-                const float a = 1.5f + 0.5f * nrm[0] * K;
-                dlo = fmaxf(dlo, (a - 3.0f - eps) * ib0);
-                dhi = fminf(dhi, (a + eps) * ib0);
-            }
-            bool row_empty = !live || c2 < lo[2] || c2 > hi[2] || c1 < lo[1] || c1 > hi[1];
-            {
-                const float a = 1.5f - D1 + 0.5f * nrm[1] * K;
-                if (use1) {
-                    const float x0 = (-eps - a) * ib1, x1 = (3.0f + eps - a) * ib1;
-                    dlo = fmaxf(dlo, fminf(x0, x1)); dhi = fminf(dhi, fmaxf(x0, x1));
-                } else if (a <= -eps - 8.0f * fabsf(b1) || a >= 3.0f + eps + 8.0f * fabsf(b1)) row_empty = true;
-            }
-            {
-                const float a = 1.5f - D2 + 0.5f * nrm[2] * K;
-                if (use2) {
-                    const float x0 = (-eps - a) * ib2, x1 = (3.0f + eps - a) * ib2;
-                    dlo = fmaxf(dlo, fminf(x0, x1)); dhi = fminf(dhi, fmaxf(x0, x1));
-                } else if (a <= -eps - 8.0f * fabsf(b2) || a >= 3.0f + eps + 8.0f * fabsf(b2)) row_empty = true;
-            }
-            if (!(dlo <= dhi)) row_empty = true;
-            const int r_lo = row_empty ? 0x7fffffff : max(lo[0], (int)floorf(p[0] - dhi - eps));
-            const int r_hi = row_empty ? (int)0x80000000 : min(hi[0], (int)ceilf(p[0] - dlo + eps));
-            const int w_lo = __reduce_min_sync(full, r_lo), w_hi = __reduce_max_sync(full, r_hi);
-            const float d1n = FMUL(nrm[1], FSUB(p[1], f1));
-            for (int c0 = w_lo; c0 <= w_hi; ++c0) {
-                const float f0 = (float)c0;
-                // dot = ((0 + n0 (p0-c0)) + n1 (p1-c1)) + n2 (p2-c2), cpp:239-240
-                float dot = FADD(0.0f, FMUL(nrm[0], FSUB(p[0], f0)));
-                dot = FADD(dot, d1n);
-                dot = FADD(dot, d2n);
-                const float fc[3] = { f0, f1, f2 };
-                const float qq[3] = { q0, q1, q2 };
-                float weight = 1.0f;
-                bool in = c0 >= r_lo && c0 <= r_hi;            // outside the lane's own interval: weight 0 by construction
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const float tt = FSUB(FADD(fc[i], FMUL(FMUL(nrm[i], dot), 0.5f)), qq[i]);
-                    in = in && tt > 0.0f && tt < 3.0f;
-                    const float t1 = FSUB(tt, 1.0f), t2 = FSUB(2.0f, tt), t3 = FSUB(3.0f, tt);
-                    const float mid = FSUB(1.0f, FMUL(FADD(FMUL(t1, t1), FMUL(t2, t2)), 0.5f));
-                    const float edge = tt < 1.0f ? tt : t3;
-                    const float piece = (tt >= 1.0f && tt < 2.0f) ? mid : FMUL(FMUL(edge, edge), 0.5f);
-                    weight = FMUL(weight, piece);
-                }
-                if (in && weight > 1e-6f)
-                    result = FADD(result, FMUL(weight, __ldg(t.N + tmod(c0, t) + i1 + i2)));
-            }
-        }
-    }
-    return result;
-}
-
 // ---- Perlin, double precision -------------------------------------------------------------------
 __device__ __forceinline__ double pfade(double t)    // t*t*t*(t*(t*6-15)+10)
 {
@@ -420,18 +313,6 @@ __global__ void k_proj(WnTileView t, C c, const float *normals, float n0, float 
     float nrm[3] = { n0, n1, n2 };
     if (normals) { nrm[0] = __ldg(normals + 3 * s); nrm[1] = __ldg(normals + 3 * s + 1); nrm[2] = __ldg(normals + 3 * s + 2); }
     out[s] = FMUL(eval3d_projected(t, p, nrm), post);
-}
-// image grids: one warp = 32 neighbouring pixels of a row, evaluated in lock step (eval3d_projected_warp)
-__global__ void __launch_bounds__(128) k_proj_grid(WnTileView t, WnAffine c, float n0, float n1, float n2, size_t first,
-                                                   size_t count, float post, float *out)
-{
-    const size_t s = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    const bool live = s < count;
-    float p[3] = { 0.0f, 0.0f, 0.0f };
-    if (live) coord(c, first + s, p);
-    const float nrm[3] = { n0, n1, n2 };
-    const float v = eval3d_projected_warp(t, p, nrm, live);
-    if (live) out[s] = FMUL(v, post);
 }
 // Cook & DeRose App. 2 WMultibandNoise(p, s, normal, firstBand, nbands, w), statement by statement: active bands b < nb_active (s + firstBand + b < 0, decided on the host), q = 2 p
 // 2^(firstBand+b) evaluated in double like the listing's pow(), result /= sqrt(variance * (normal ? 0.296 : 0.210)).
@@ -598,9 +479,7 @@ int wn_launch_proj_affine(WnTileView t, WnAffine c, const float nrm[3], size_t f
                           float *out, cudaStream_t st)
 {
     if (!count) return 0;
-    static const bool per_lane = [] { const char *e = getenv("WN_PROJ_WARP"); return e && atoi(e) == 0; }();   // A/B runs
-    if (per_lane) k_proj<WnAffine><<<blocks_for(count, 128), 128, 0, st>>>(t, c, nullptr, nrm[0], nrm[1], nrm[2], first, count, post, out);
-    else k_proj_grid<<<blocks_for(count, 128), 128, 0, st>>>(t, c, nrm[0], nrm[1], nrm[2], first, count, post, out);
+    k_proj<WnAffine><<<blocks_for(count, 128), 128, 0, st>>>(t, c, nullptr, nrm[0], nrm[1], nrm[2], first, count, post, out);
     return 1;
 }
 int wn_launch_perlin_points(const int32_t *perm, WnPointsAoS c, size_t first, size_t count, float *out, int fast, cudaStream_t st)
