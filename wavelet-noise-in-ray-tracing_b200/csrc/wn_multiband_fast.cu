@@ -852,13 +852,12 @@ __device__ __forceinline__ void q4_footprints_rep(const float4 *s_tab, int nband
         }
         ft.row0[nbands] = row0;
     }
-    static_assert(BZ <= 32, "one lane per z step, two mask bits per step");
-    if (threadIdx.x < 32) {                                    // advance masks (one lane per z step)
+    if (threadIdx.x < 32) {                                    // advance masks (BZ == 32 steps, one lane per step)
         int slow = 0;
         for (int b = 0; b < nbands && b < 2; ++b) {
             const float4 *tZ = s_tab + b * PER_BAND + BX + BY;
             const int k = threadIdx.x;
-            const int a = (k == 0 || k >= BZ) ? 0 : __float_as_int(tZ[k].w) - __float_as_int(tZ[k - 1].w);
+            const int a = k == 0 ? 0 : __float_as_int(tZ[k].w) - __float_as_int(tZ[k - 1].w);
             slow |= __any_sync(0xffffffffu, a > 3 || a < 0);
             unsigned long long m = (unsigned long long)(a & 3) << (2 * k);
 #pragma unroll
@@ -969,13 +968,12 @@ constexpr int rep_min_blocks(int windows) { return windows <= 2 ? 3 : 2; }
 
 // NB direct bands; the last NSH of them are shared by the replicas (see q4_footprints_rep), the others have one window
 // per replica
-template <int NB, int NSH, int RX, int RY, int YPW, int RINGMODE, int BZ, bool POW2>
+template <int NB, int NSH, int RX, int RY, int YPW, int RINGMODE, bool POW2>
 __global__ void __launch_bounds__(256, rep_min_blocks((NB - NSH) * RX * RY + NSH))
 k_mb3d_rep(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int nk, int max_rows, WnFold fold,
            WnOrder ord, WnRep rep, const __grid_constant__ CUtensorMap pmap, float *__restrict__ out)
 {
-    constexpr int BX = 128, BY = 8, NT = 256, R = RX * RY;      // BZ = 32, or 16 when a grid of 32-deep bricks fills the
-                                                                // last wave of CTAs badly (small shards, see rep_pass)
+    constexpr int BX = 128, BY = 8, BZ = 32, NT = 256, R = RX * RY;
     constexpr int RING = NB == 1 ? 8 : 4;                       // period-block planes in flight (two bands: U needs the room)
     constexpr int HP = RING / 2;                                // RINGMODE 1: planes per TMA box = half a ring
     constexpr int PER_BAND = BX + BY + BZ;
@@ -1510,12 +1508,12 @@ bool make_period_map(const float *P, int Lx, int Ly, int Lz, int planes, CUtenso
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int NB, int NSH, int RX, int RY, int YPW, int RINGMODE, int BZ>
+template <int NB, int NSH, int RX, int RY, int YPW, int RINGMODE>
 int launch_rep(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk, float *out, int max_rows, size_t smem, WnFold fold,
                const WnRep &rep, const CUtensorMap &pmap, cudaStream_t st)
 {
-    constexpr int BY = 8, NT = 256;
-    auto kern = t.pow2 ? k_mb3d_rep<NB, NSH, RX, RY, YPW, RINGMODE, BZ, true> : k_mb3d_rep<NB, NSH, RX, RY, YPW, RINGMODE, BZ, false>;
+    constexpr int BY = 8, BZ = 32, NT = 256;
+    auto kern = t.pow2 ? k_mb3d_rep<NB, NSH, RX, RY, YPW, RINGMODE, true> : k_mb3d_rep<NB, NSH, RX, RY, YPW, RINGMODE, false>;
     if (!allow_smem(kern, smem)) return -1;
     const int nyb = (rep.by + BY - 1) / BY, nzb = (nk + BZ - 1) / BZ;
     WnOrder ord{1, nyb, 1, nzb};
@@ -1573,27 +1571,16 @@ int rep_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsigned
             }
         const int windows = (nb - nsh) * R + nsh;
         if (windows > (nsh ? 5 : 4)) continue;
-        // brick depth: 32 z steps, or 16 when that fills the last wave of CTAs (two per SM) clearly better -- the shards
-        // of an 8-GPU run are 3.5 waves of 32-deep bricks, i.e. four waves of time for 3.5 waves of work
-        int bz = 32;
-        {
-            const double slots = 2.0 * 148.0;
-            const double ctas32 = (double)((rep.bx + 127) / 128) * ((rep.by + 7) / 8) * ((nk + 31) / 32);
-            const double ctas16 = (double)((rep.bx + 127) / 128) * ((rep.by + 7) / 8) * ((nk + 15) / 16);
-            const double w32 = ctas32 / slots, w16 = ctas16 / slots;
-            if (w32 < 12.0 && std::ceil(w32) / w32 > 1.06 * std::ceil(w16) / w16) bz = 16;
-            if (const char *e = getenv("WN_REP_BZ")) bz = atoi(e) == 16 ? 16 : 32;
-        }
         int max_rows = 0;
         bool ok = true;
         for (int i = 0; i < nb && ok; ++i) {
-            const BrickPlan pb = plan_bricks(h, rows + i, 1, rep.by, k0, nk, 8, bz, 128, true);
+            const BrickPlan pb = plan_bricks(h, rows + i, 1, rep.by, k0, nk, 8, 32, 128, true);
             ok = pb.ok;
             max_rows += pb.max_rows * (i < nb - nsh ? R : 1);
         }
         if (!ok) return 0;                                     // unsorted axes / huge footprints: not a brick lattice
         const size_t smem = ring_bytes + (size_t)max_rows * (128 * sizeof(float) + sizeof(int)) +
-                            (size_t)nb * (128 + 8 + bz) * sizeof(float4) + 64;
+                            (size_t)nb * (128 + 8 + 32) * sizeof(float4) + 64;
         if (smem > 113 * 1024) continue;
         int ypw = 1, tma = 1;
         if (const char *e = getenv("WN_REP_YPW")) ypw = (atoi(e) == 4 && nb == 1) ? 4 : 1;
@@ -1601,18 +1588,16 @@ int rep_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsigned
         CUtensorMap pmap;
         std::memset(&pmap, 0, sizeof(pmap));
         tma = tma && fold.P && fold.Lx % 128 == 0 && fold.Ly % 8 == 0 && fold.Lz % 4 == 0 && fold.kphase % 4 == 0 &&
-              rep.bx % 128 == 0 && rep.by % 8 == 0 && nk % bz == 0 &&
+              rep.bx % 128 == 0 && rep.by % 8 == 0 && nk % 32 == 0 &&
               make_period_map(fold.P, fold.Lx, fold.Ly, fold.Lz, ring_planes / 2, &pmap);
         for (int r = 0; r < 4; ++r)
             rep.roff[r] = 4LL * ((long long)(r % RX) * rep.bx + (long long)nx * ((long long)(r / RX) * rep.by));
-#define WN_REP_CASE(NB_, NSH_, RX_, RY_, YPW_, TMA_, BZ_)                                                                \
-        if (nb == NB_ && nsh == NSH_ && RX == RX_ && RY == RY_ && ypw == YPW_ && tma == TMA_ && bz == BZ_)              \
-            return launch_rep<NB_, NSH_, RX_, RY_, YPW_, TMA_, BZ_>(t, tabs, nx, ny, nk, out, max_rows, smem, fold, rep, pmap, st);
-#define WN_REP_CASES(NB_, NSH_, RX_, RY_) \
-        WN_REP_CASE(NB_, NSH_, RX_, RY_, 1, 1, 32) WN_REP_CASE(NB_, NSH_, RX_, RY_, 1, 0, 32) \
-        WN_REP_CASE(NB_, NSH_, RX_, RY_, 1, 1, 16) WN_REP_CASE(NB_, NSH_, RX_, RY_, 1, 0, 16)
+#define WN_REP_CASE(NB_, NSH_, RX_, RY_, YPW_, TMA_)                                                                     \
+        if (nb == NB_ && nsh == NSH_ && RX == RX_ && RY == RY_ && ypw == YPW_ && tma == TMA_)                           \
+            return launch_rep<NB_, NSH_, RX_, RY_, YPW_, TMA_>(t, tabs, nx, ny, nk, out, max_rows, smem, fold, rep, pmap, st);
+#define WN_REP_CASES(NB_, NSH_, RX_, RY_) WN_REP_CASE(NB_, NSH_, RX_, RY_, 1, 1) WN_REP_CASE(NB_, NSH_, RX_, RY_, 1, 0)
         WN_REP_CASES(1, 0, 1, 1) WN_REP_CASES(1, 0, 1, 2) WN_REP_CASES(1, 0, 2, 2)
-        WN_REP_CASE(1, 0, 1, 2, 4, 1, 32) WN_REP_CASE(1, 0, 1, 2, 4, 0, 32)
+        WN_REP_CASE(1, 0, 1, 2, 4, 1) WN_REP_CASE(1, 0, 1, 2, 4, 0)
         WN_REP_CASES(2, 0, 1, 1) WN_REP_CASES(2, 0, 1, 2)
         WN_REP_CASES(2, 1, 1, 2) WN_REP_CASES(2, 1, 2, 2)
 #undef WN_REP_CASES
