@@ -915,7 +915,9 @@ extern "C" int wn_multiband3d_lattice(const wn_tile *t, const float *xs, int nx,
     // Measured on config 3 shards: 157 -> 147 us (1/8 of the volume), 291 -> 280 us (1/4), 575 -> 557 us (1/2), but
     // 1.12 -> 1.14 ms for the whole 1024^3, where the chain is bandwidth- rather than latency-bound and only competes
     // with the main kernel for DRAM: the side stream is used up to 2^29 samples per call.
-    const bool use_side = mode == WN_EVAL_FAST && space == WN_DEVICE && side_env && total <= ((size_t)1 << 29);
+    size_t side_max = (size_t)1 << 29;
+    if (const char *e = getenv("WN_SIDE_MAX_LOG2")) side_max = (size_t)1 << atoi(e);     // read per call (A/B runs)
+    const bool use_side = mode == WN_EVAL_FAST && space == WN_DEVICE && side_env && total <= side_max;
     ParamWriter pw(c, use_side);
     if ((r = pw.reserve(((size_t)nx + ny + nz) * sizeof(float) + 2048))) return r;
     WnLattice L{nullptr, nullptr, nullptr, nx, ny, nz};
