@@ -17,10 +17,16 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 int wn_set_error(int code, const char *fmt, ...);               // wn_capi.cu: fills the thread's wn_last_error text
@@ -57,6 +63,36 @@ const int kNcclFloat = 7;                                        // ncclFloat32 
 
 struct RankBuf { float *p = nullptr; size_t cap = 0; };          // floats
 
+// One host thread per GPU of a group: planning and enqueueing a rank's share of a call costs tens of microseconds of
+// host time, which a single thread would pay N times in a row while the GPUs wait (measured: 8 ranks enqueued by one
+// thread = 0.41 ms per 1024^3 call, slower than 4).  The caller's thread hands every rank's closure to its worker and
+// waits for all of them to have ENQUEUED; the GPU work itself stays asynchronous.
+struct Worker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool has_job = false, stop = false;
+    int rc = 0;
+    std::string err;
+    void loop(int device)
+    {
+        cudaSetDevice(device);
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [&] { return has_job || stop; });
+            if (stop) return;
+            lk.unlock();
+            const int r = job();
+            std::string e = r != WN_OK ? wn_last_error() : "";
+            lk.lock();
+            rc = r; err.swap(e);
+            has_job = false;
+            cv.notify_all();
+        }
+    }
+};
+
 // the group functions switch the current device while they enqueue; the caller's device is restored on return
 struct DeviceRestore {
     int d = 0;
@@ -75,6 +111,7 @@ struct wn_group {
     std::vector<RankBuf> out, in;                                // per-rank device output / input shards
     std::vector<size_t> out_count;                               // floats of the last sharded call per rank
     std::vector<cudaEvent_t> ev0, ev1;                           // timing of the last sharded call per rank
+    std::vector<std::unique_ptr<Worker>> workers;               // one per rank when n > 1
 };
 
 struct wn_gtile {
@@ -142,22 +179,31 @@ std::vector<int> shard_indices(int total, int rank, int world, int sharding)
     return idx;
 }
 
-int begin_timing(wn_group *g)
+// f(rank) for every rank, concurrently on the rank workers (inline for a one-GPU group); returns the first failure
+template <class F>
+int for_ranks(wn_group *g, F f)
 {
-    for (int r = 0; r < g->n; ++r) {
-        WG_CUDA(cudaSetDevice(g->dev[r]));
-        WG_CUDA(cudaEventRecord(g->ev0[r], wn_ctx_stream_internal(g->ctx[r])));
+    if (g->workers.empty()) {
+        for (int r = 0; r < g->n; ++r) WG_OK(f(r));
+        return WN_OK;
     }
-    return WN_OK;
-}
-int end_timing(wn_group *g)
-{
     for (int r = 0; r < g->n; ++r) {
-        WG_CUDA(cudaSetDevice(g->dev[r]));
-        WG_CUDA(cudaEventRecord(g->ev1[r], wn_ctx_stream_internal(g->ctx[r])));
+        Worker &w = *g->workers[r];
+        std::lock_guard<std::mutex> lk(w.m);
+        w.job = [&f, r] { return f(r); };
+        w.has_job = true;
+        w.cv.notify_all();
     }
-    return WN_OK;
+    int rc = WN_OK;
+    for (int r = 0; r < g->n; ++r) {
+        Worker &w = *g->workers[r];
+        std::unique_lock<std::mutex> lk(w.m);
+        w.cv.wait(lk, [&] { return !w.has_job; });
+        if (w.rc != WN_OK && rc == WN_OK) rc = wn_set_error(w.rc, "%s", w.err.c_str());
+    }
+    return rc;
 }
+
 // waits for every rank; *ms (nullable) = max over ranks of the GPU time between begin_timing and end_timing
 int finish(wn_group *g, float *ms)
 {
@@ -212,6 +258,13 @@ extern "C" int wn_group_create(int ngpus, const int *devices, wn_group **out)
     }
     cudaSetDevice(prev);
     if (rc != WN_OK) { wn_group_destroy(g); return rc; }
+    if (ngpus > 1)
+        for (int r = 0; r < ngpus; ++r) {
+            g->workers.emplace_back(new Worker());
+            Worker *w = g->workers.back().get();
+            const int device = g->dev[r];
+            w->th = std::thread([w, device] { w->loop(device); });
+        }
     *out = g;
     return WN_OK;
 }
@@ -219,6 +272,11 @@ extern "C" int wn_group_create(int ngpus, const int *devices, wn_group **out)
 extern "C" int wn_group_destroy(wn_group *g)
 {
     if (!g) return WN_OK;
+    for (auto &w : g->workers) {
+        { std::lock_guard<std::mutex> lk(w->m); w->stop = true; w->cv.notify_all(); }
+        if (w->th.joinable()) w->th.join();
+    }
+    g->workers.clear();
     int prev = 0;
     cudaGetDevice(&prev);
     for (int r = 0; r < g->n; ++r) {
@@ -351,27 +409,27 @@ extern "C" int wn_group_multiband3d_lattice(wn_gtile *t, const float *xs, int nx
         WG_OK(reserve(g, g->out, r, slice * idx[r].size()));
         g->out_count[r] = slice * idx[r].size();
     }
-    WG_OK(begin_timing(g));
-    for (int r = 0; r < g->n; ++r) {                              // enqueue on every GPU before waiting for any
-        if (idx[r].empty()) continue;
-        WG_OK(wn_multiband3d_lattice(t->t[r], xs, nx, ys, ny, zr[r].data(), (int)zr[r].size(), band_scale, weights, nbands,
-                                     post, mode, g->out[r].p, WN_DEVICE));
-    }
-    WG_OK(end_timing(g));
-    if (out_host) {                                              // gather for file output: runs of consecutive slices
-        for (int r = 0; r < g->n; ++r) {
-            WG_CUDA(cudaSetDevice(g->dev[r]));
+    // every rank plans and enqueues its share on its own host thread: timing event, kernels, timing event, gather copies
+    WG_OK(for_ranks(g, [&](int r) -> int {
+        cudaStream_t st = wn_ctx_stream_internal(g->ctx[r]);
+        WG_CUDA(cudaSetDevice(g->dev[r]));
+        WG_CUDA(cudaEventRecord(g->ev0[r], st));
+        if (!idx[r].empty())
+            WG_OK(wn_multiband3d_lattice(t->t[r], xs, nx, ys, ny, zr[r].data(), (int)zr[r].size(), band_scale, weights, nbands,
+                                         post, mode, g->out[r].p, WN_DEVICE));
+        WG_CUDA(cudaEventRecord(g->ev1[r], st));
+        if (out_host) {                                          // gather for file output: runs of consecutive slices
             size_t k = 0;
             while (k < idx[r].size()) {
                 size_t e = k + 1;
                 while (e < idx[r].size() && idx[r][e] == idx[r][e - 1] + 1) ++e;
                 WG_CUDA(cudaMemcpyAsync(out_host + slice * (size_t)idx[r][k], g->out[r].p + slice * k,
-                                        slice * (e - k) * sizeof(float), cudaMemcpyDeviceToHost,
-                                        wn_ctx_stream_internal(g->ctx[r])));
+                                        slice * (e - k) * sizeof(float), cudaMemcpyDeviceToHost, st));
                 k = e;
             }
         }
-    }
+        return WN_OK;
+    }));
     return finish(g, gpu_ms);
 }
 
@@ -389,19 +447,19 @@ extern "C" int wn_group_eval3d_projected_grid(wn_gtile *t, const float origin[3]
         WG_OK(reserve(g, g->out, r, (size_t)nu * (e[r] - b[r])));
         g->out_count[r] = (size_t)nu * (e[r] - b[r]);
     }
-    WG_OK(begin_timing(g));
-    for (int r = 0; r < g->n; ++r)
+    WG_OK(for_ranks(g, [&](int r) -> int {
+        cudaStream_t st = wn_ctx_stream_internal(g->ctx[r]);
+        WG_CUDA(cudaSetDevice(g->dev[r]));
+        WG_CUDA(cudaEventRecord(g->ev0[r], st));
         if (e[r] > b[r])
             WG_OK(wn_eval3d_projected_grid(t->t[r], origin, e1, us, nu, e2, vs + b[r], (int)(e[r] - b[r]), normal, pre, post,
                                            g->out[r].p, WN_DEVICE));
-    WG_OK(end_timing(g));
-    if (out_host)
-        for (int r = 0; r < g->n; ++r) {
-            if (e[r] == b[r]) continue;
-            WG_CUDA(cudaSetDevice(g->dev[r]));
+        WG_CUDA(cudaEventRecord(g->ev1[r], st));
+        if (out_host && e[r] > b[r])
             WG_CUDA(cudaMemcpyAsync(out_host + (size_t)nu * b[r], g->out[r].p, g->out_count[r] * sizeof(float),
-                                    cudaMemcpyDeviceToHost, wn_ctx_stream_internal(g->ctx[r])));
-        }
+                                    cudaMemcpyDeviceToHost, st));
+        return WN_OK;
+    }));
     return finish(g, gpu_ms);
 }
 
@@ -417,19 +475,19 @@ extern "C" int wn_group_perlin_grid(wn_group *g, wn_perlin *const *perlin_per_ra
         WG_OK(reserve(g, g->out, r, (size_t)nu * (e[r] - b[r])));
         g->out_count[r] = (size_t)nu * (e[r] - b[r]);
     }
-    WG_OK(begin_timing(g));
-    for (int r = 0; r < g->n; ++r)
+    WG_OK(for_ranks(g, [&](int r) -> int {
+        cudaStream_t st = wn_ctx_stream_internal(g->ctx[r]);
+        WG_CUDA(cudaSetDevice(g->dev[r]));
+        WG_CUDA(cudaEventRecord(g->ev0[r], st));
         if (e[r] > b[r])
             WG_OK(wn_perlin_grid(perlin_per_rank[r], origin, e1, us, nu, e2, vs + b[r], (int)(e[r] - b[r]), pre, g->out[r].p,
                                  WN_DEVICE));
-    WG_OK(end_timing(g));
-    if (out_host)
-        for (int r = 0; r < g->n; ++r) {
-            if (e[r] == b[r]) continue;
-            WG_CUDA(cudaSetDevice(g->dev[r]));
+        WG_CUDA(cudaEventRecord(g->ev1[r], st));
+        if (out_host && e[r] > b[r])
             WG_CUDA(cudaMemcpyAsync(out_host + (size_t)nu * b[r], g->out[r].p, g->out_count[r] * sizeof(float),
-                                    cudaMemcpyDeviceToHost, wn_ctx_stream_internal(g->ctx[r])));
-        }
+                                    cudaMemcpyDeviceToHost, st));
+        return WN_OK;
+    }));
     return finish(g, gpu_ms);
 }
 
@@ -449,17 +507,19 @@ extern "C" int wn_group_wavelet_texture_values(wn_gtile *t, const float *p_host,
         WG_OK(reserve(g, g->out, r, e[r] - b[r]));
         g->out_count[r] = e[r] - b[r];
     }
-    WG_OK(begin_timing(g));
-    for (int r = 0; r < g->n; ++r) {
+    WG_OK(for_ranks(g, [&](int r) -> int {
         const size_t cnt = e[r] - b[r];
-        if (!cnt) continue;
-        WG_CUDA(cudaSetDevice(g->dev[r]));
         cudaStream_t st = wn_ctx_stream_internal(g->ctx[r]);
-        WG_CUDA(cudaMemcpyAsync(g->in[r].p, p_host + 3 * b[r], 3 * cnt * sizeof(float), cudaMemcpyHostToDevice, st));
-        WG_OK(wn_wavelet_texture_values(t->t[r], g->in[r].p, cnt, scale, octave, g->out[r].p, WN_DEVICE));
-        WG_CUDA(cudaMemcpyAsync(grey_host + b[r], g->out[r].p, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
-    }
-    WG_OK(end_timing(g));
+        WG_CUDA(cudaSetDevice(g->dev[r]));
+        WG_CUDA(cudaEventRecord(g->ev0[r], st));
+        if (cnt) {
+            WG_CUDA(cudaMemcpyAsync(g->in[r].p, p_host + 3 * b[r], 3 * cnt * sizeof(float), cudaMemcpyHostToDevice, st));
+            WG_OK(wn_wavelet_texture_values(t->t[r], g->in[r].p, cnt, scale, octave, g->out[r].p, WN_DEVICE));
+            WG_CUDA(cudaMemcpyAsync(grey_host + b[r], g->out[r].p, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        WG_CUDA(cudaEventRecord(g->ev1[r], st));
+        return WN_OK;
+    }));
     return wait ? finish(g, nullptr) : WN_OK;
 }
 
@@ -475,16 +535,18 @@ extern "C" int wn_group_perlin_texture_values(wn_group *g, wn_perlin *const *per
         WG_OK(reserve(g, g->out, r, e[r] - b[r]));
         g->out_count[r] = e[r] - b[r];
     }
-    WG_OK(begin_timing(g));
-    for (int r = 0; r < g->n; ++r) {
+    WG_OK(for_ranks(g, [&](int r) -> int {
         const size_t cnt = e[r] - b[r];
-        if (!cnt) continue;
-        WG_CUDA(cudaSetDevice(g->dev[r]));
         cudaStream_t st = wn_ctx_stream_internal(g->ctx[r]);
-        WG_CUDA(cudaMemcpyAsync(g->in[r].p, p_host + 3 * b[r], 3 * cnt * sizeof(float), cudaMemcpyHostToDevice, st));
-        WG_OK(wn_perlin_texture_values(perlin_per_rank[r], g->in[r].p, cnt, scale, octave, g->out[r].p, WN_DEVICE));
-        WG_CUDA(cudaMemcpyAsync(grey_host + b[r], g->out[r].p, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
-    }
-    WG_OK(end_timing(g));
+        WG_CUDA(cudaSetDevice(g->dev[r]));
+        WG_CUDA(cudaEventRecord(g->ev0[r], st));
+        if (cnt) {
+            WG_CUDA(cudaMemcpyAsync(g->in[r].p, p_host + 3 * b[r], 3 * cnt * sizeof(float), cudaMemcpyHostToDevice, st));
+            WG_OK(wn_perlin_texture_values(perlin_per_rank[r], g->in[r].p, cnt, scale, octave, g->out[r].p, WN_DEVICE));
+            WG_CUDA(cudaMemcpyAsync(grey_host + b[r], g->out[r].p, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        WG_CUDA(cudaEventRecord(g->ev1[r], st));
+        return WN_OK;
+    }));
     return wait ? finish(g, nullptr) : WN_OK;
 }
