@@ -280,8 +280,9 @@ int  wn_group_tile_upload(wn_gtile *t, const float *N_host);
 int  wn_group_tile_rank(wn_gtile *t, int rank, wn_tile **tile);
 /* wn_multiband3d_lattice sharded along z (BASELINE config 3).  The shards stay on the devices (wn_group_shard); when
  * out_host is not NULL the volume is also gathered there in the lattice layout (pinned memory recommended).  *gpu_ms
- * (nullable) = max over the GPUs of the CUDA-event time of the enqueued kernels.  Results are bit-identical to the
- * single-GPU call for either sharding (canonical summation, see wn_multiband3d_lattice). */
+ * (nullable) = max over the GPUs of the CUDA-event time of the enqueued kernels.  With out_host == NULL and gpu_ms ==
+ * NULL the call only enqueues (wn_group_synchronize waits), so back-to-back calls keep every GPU busy.  Results are
+ * bit-identical to the single-GPU call for either sharding (canonical summation, see wn_multiband3d_lattice). */
 int  wn_group_multiband3d_lattice(wn_gtile *t, const float *xs, int nx, const float *ys, int ny, const float *zs, int nz,
                                   const float *band_scale, const float *weights, int nbands, float post_scale, int mode,
                                   int sharding, float *out_host, float *gpu_ms);

@@ -103,6 +103,14 @@ static int run_volume(const Args &a)
         sum_ms += gpu_ms;
     }
     const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / reps;
+    // throughput: the same calls enqueued back to back without waiting in between (the shards stay on the devices)
+    CHECK(wn_group_synchronize(g));
+    t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < 4 * reps; ++r)
+        CHECK(wn_group_multiband3d_lattice(t, ax.data(), S, ax.data(), S, ax.data(), S, scale.data(), w.data(), (int)w.size(),
+                                           post, WN_EVAL_FAST, sharding, nullptr, nullptr));
+    CHECK(wn_group_synchronize(g));
+    const double stream_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / (4 * reps);
     double gather_ms = 0.0;
     uint64_t hash = 0;
     if (gather) {
@@ -119,10 +127,12 @@ static int run_volume(const Args &a)
     }
     std::printf("{\"driver\": \"sharded_b200 volume\", \"config\": \"WMultibandNoise %d^3 bands %d-%d tile n=%d seed %u\", "
                 "\"n_gpus\": %d, \"sharding\": \"%s\", \"reps\": %d, \"gpu_ms_mean\": %.4f, \"gpu_ms_best\": %.4f, "
-                "\"wall_ms_per_call\": %.4f, \"gsamples_s\": %.2f, \"gsamples_s_wall\": %.2f, \"tile_build_and_broadcast_ms\": %.3f, "
+                "\"wall_ms_per_call\": %.4f, \"gsamples_s\": %.2f, \"gsamples_s_wall\": %.2f, \"back_to_back_ms_per_call\": %.4f, "
+                "\"gsamples_s_back_to_back\": %.2f, \"tile_build_and_broadcast_ms\": %.3f, "
                 "\"gather_ms\": %.2f, \"fnv1a64\": \"%016llx\"}\n",
                 S, a.b0, a.b1, a.tile, a.seed, N, a.sharding.c_str(), reps, sum_ms / reps, best_ms, wall_ms,
-                (double)total / (sum_ms / reps) / 1e6, (double)total / wall_ms / 1e6, tile_ms, gather_ms,
+                (double)total / (sum_ms / reps) / 1e6, (double)total / wall_ms / 1e6, stream_ms, (double)total / stream_ms / 1e6,
+                tile_ms, gather_ms,
                 (unsigned long long)hash);
     if (host) wn_host_free(host);
     wn_group_tile_destroy(t);

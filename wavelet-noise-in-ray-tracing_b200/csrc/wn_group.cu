@@ -430,6 +430,7 @@ extern "C" int wn_group_multiband3d_lattice(wn_gtile *t, const float *xs, int nx
         }
         return WN_OK;
     }));
+    if (!out_host && !gpu_ms) return WN_OK;                     // enqueue only: the caller synchronises the group later
     return finish(g, gpu_ms);
 }
 
