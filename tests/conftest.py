@@ -11,6 +11,11 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a kernel that never returns must fail the test, not hang the box: with pytest-timeout present every test gets a
+    # generous limit unless the command line sets one (the slowest test, the unmodified reference driver making 983 040
+    # one-point launches, takes about a minute)
+    if config.pluginmanager.hasplugin("timeout") and not getattr(config.option, "timeout", None):
+        config.option.timeout = 1500
 
 
 @pytest.fixture(scope="session")

@@ -16,6 +16,8 @@
 // The tile (8 MiB at n = 128) stays L2-resident; taps are read through the read-only path.
 #include "wn_internal.h"
 
+#include <cstdlib>
+
 namespace {
 
 #define FMUL __fmul_rn
@@ -333,6 +335,148 @@ __global__ void k_wmultiband(WnTileView t, const float *p, size_t count, WnBands
     out[s] = result;
 }
 
+// Image grids: the 32 lanes of a warp are neighbouring pixels, a fraction of a tile cell apart, so they weigh almost
+// the same cells.  Per lane, eval3d_projected() spends most of its instructions FINDING its ~52 contributing cells (row
+// bounds for every row of its bounding box) and the lanes' loops diverge (ncu: 25 of 32 lanes active).  Here the warp
+// builds ONE candidate list cooperatively -- each lane tests one cell of the union bounding box per round against the
+// exact support region A (c - p) in (-1.5, 1.5)^3, A = I - n n^T / 2, widened by the extent of the warp's points and a
+// rounding slack, compacted with ballots in the reference's visiting order (z outer, x inner) into shared memory --
+// and then every lane evaluates every listed cell for its own point with the reference's arithmetic (cpp:239-260).  A
+// listed cell that is outside a lane's own reference box, or that the reference weighs with 0, contributes nothing, so
+// each lane adds its contributing cells in the reference's order: bit-identical to eval3d_projected().
+constexpr int PROJ_LIST = 192;                                 // candidate cells per warp (config 4 needs ~95)
+
+__global__ void __launch_bounds__(128, 8) k_proj_grid(WnTileView t, WnAffine c, float n0, float n1, float n2, size_t first,
+                                                   size_t count, float post, float *out)
+{
+    __shared__ int2 s_list[4][PROJ_LIST];                      // {cell relative to the union box (4 bits per axis... 5), tile index}
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // a warp owns an 8 x 4 patch of pixels (not 32 pixels of one row): its points are closer together, so the union of
+    // their candidate cells is smaller (about 1.15x a single point's instead of 1.6x)
+    const size_t row0 = first / (size_t)c.nu;                  // first image row of this launch's sample window
+    const int patches_x = (c.nu + 7) / 8;
+    const size_t wid = blockIdx.x * (size_t)(blockDim.x >> 5) + warp;
+    const size_t pi = (wid % patches_x) * 8 + (lane & 7), pj = row0 + (wid / patches_x) * 4 + (lane >> 3);
+    const size_t sg = pi + (size_t)c.nu * pj;                  // global sample index
+    bool live = pi < (size_t)c.nu && pj < (size_t)c.nv && sg >= first && sg < first + count;
+    const bool store = live;
+    const size_t s = sg - first;
+    const unsigned livemask = __ballot_sync(full, live);
+    if (!livemask) return;
+    float p[3] = { 0.0f, 0.0f, 0.0f };
+    if (live) coord(c, sg, p);
+    const float nrm[3] = { n0, n1, n2 };
+    // the reference's own box of this lane (cpp:228-232)
+    int lo[3], hi[3];
+    float sup[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        sup[i] = FADD(FMUL(3.0f, fabsf(nrm[i])), FMUL(3.0f, __fsqrt_rn(FMUL(FSUB(1.0f, FMUL(nrm[i], nrm[i])), 0.5f))));
+        lo[i] = (int)ceilf(FSUB(p[i], sup[i]));
+        hi[i] = (int)floorf(FADD(p[i], sup[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        if (hi[i] - lo[i] > 12 || hi[i] < lo[i] - 1 || hi[i] == 0x7fffffff) live = false;     // see eval3d_projected
+    const unsigned okmask = __ballot_sync(full, live);
+    float result = 0.0f;
+    if (okmask) {
+        // union box and the extent of the warp's points (dead lanes borrow a live lane's values)
+        const int src = __ffs((int)okmask) - 1;
+        int ulo[3], uhi[3];
+        float pc[3], hw[3];
+        float pmax = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float borrowed = __shfl_sync(full, p[i], src);       // executed by every lane (never inside a branch)
+            const float pl = live ? p[i] : borrowed;
+            float mn = pl, mx = pl;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn = fminf(mn, __shfl_xor_sync(full, mn, o));
+                mx = fmaxf(mx, __shfl_xor_sync(full, mx, o));
+            }
+            pc[i] = 0.5f * (mn + mx);
+            hw[i] = 0.5f * (mx - mn);
+            ulo[i] = __reduce_min_sync(full, live ? lo[i] : 0x7fffffff);
+            uhi[i] = __reduce_max_sync(full, live ? hi[i] : (int)0x80000000);
+            pmax = fmaxf(pmax, fmaxf(fabsf(mn), fabsf(mx)));
+        }
+        const int e0 = uhi[0] - ulo[0] + 1, e1 = uhi[1] - ulo[1] + 1, e2 = uhi[2] - ulo[2] + 1;
+        const int total = e0 * e1 * e2;
+        // every live lane has the union box as its own box (the usual case): no per-candidate box test needed
+        const bool samebox = __all_sync(full, !live || (lo[0] == ulo[0] && hi[0] == uhi[0] && lo[1] == ulo[1] && hi[1] == uhi[1] &&
+                                                         lo[2] == ulo[2] && hi[2] == uhi[2]));
+        int listed = PROJ_LIST + 1;                            // > PROJ_LIST: fall back to the per-lane walk
+        if (e0 <= 32 && e1 <= 32 && e2 <= 32 && total <= 8192) {
+            // |A (c - p)|_i < 1.5 for some lane  =>  |A (c - pc)|_i < 1.5 + sum_j |A_ij| hw_j (+ rounding slack)
+            const float eps = (pmax + 16.0f) * 4.0e-6f + 1.0e-4f;
+            float bound[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                float sl = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) sl += fabsf((i == j ? 1.0f : 0.0f) - 0.5f * nrm[i] * nrm[j]) * hw[j];
+                bound[i] = 1.5f + sl + eps;
+            }
+            listed = 0;
+            for (int base = 0; base < total; base += 32) {
+                const int idx = base + lane;
+                const int z = idx / (e0 * e1), r = idx - z * (e0 * e1), y = r / e0, x = r - y * e0;
+                const float d0 = (float)(ulo[0] + x) - pc[0], d1 = (float)(ulo[1] + y) - pc[1], d2 = (float)(ulo[2] + z) - pc[2];
+                const float m = 0.5f * (nrm[0] * d0 + nrm[1] * d1 + nrm[2] * d2);
+                const bool keep = idx < total && fabsf(d0 - nrm[0] * m) < bound[0] && fabsf(d1 - nrm[1] * m) < bound[1] &&
+                                  fabsf(d2 - nrm[2] * m) < bound[2];
+                const unsigned km = __ballot_sync(full, keep);
+                const int pos = listed + __popc(km & ((1u << lane) - 1u));
+                if (keep && pos < PROJ_LIST)
+                    s_list[warp][pos] = make_int2(x | (y << 5) | (z << 10),
+                                                  tmod(ulo[0] + x, t) + tmod(ulo[1] + y, t) * t.n + tmod(ulo[2] + z, t) * t.n * t.n);
+                listed += __popc(km);
+            }
+            __syncwarp();
+        }
+        if (listed > PROJ_LIST) {
+            if (live) result = eval3d_projected(t, p, nrm);   // incoherent warp (not an image grid after all)
+        } else if (live) {
+            const float q0 = FSUB(p[0], 1.5f), q1 = FSUB(p[1], 1.5f), q2 = FSUB(p[2], 1.5f);
+            for (int k = 0; k < listed; ++k) {
+                const int2 e = s_list[warp][k];
+                const int c0 = ulo[0] + (e.x & 31), c1 = ulo[1] + ((e.x >> 5) & 31), c2 = ulo[2] + (e.x >> 10);
+                // the reference only visits its own box (cpp:235-237)
+                if (!samebox && (c0 < lo[0] || c0 > hi[0] || c1 < lo[1] || c1 > hi[1] || c2 < lo[2] || c2 > hi[2])) continue;
+                const float f0 = (float)c0, f1 = (float)c1, f2 = (float)c2;
+                // dot = ((0 + n0 (p0-c0)) + n1 (p1-c1)) + n2 (p2-c2), cpp:239-240
+                float dot = FADD(0.0f, FMUL(nrm[0], FSUB(p[0], f0)));
+                dot = FADD(dot, FMUL(nrm[1], FSUB(p[1], f1)));
+                dot = FADD(dot, FMUL(nrm[2], FSUB(p[2], f2)));
+                float weight = 1.0f;
+                const float fc[3] = { f0, f1, f2 };
+                const float qq[3] = { q0, q1, q2 };
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    // t = (c_i + n_i*dot/2) - (p_i - 1.5), cpp:245
+                    const float tt = FSUB(FADD(fc[i], FMUL(FMUL(nrm[i], dot), 0.5f)), qq[i]);
+                    if (tt <= 0.0f || tt >= 3.0f) { weight = 0.0f; break; }
+                    float piece;
+                    if (tt < 1.0f) piece = FMUL(FMUL(tt, tt), 0.5f);
+                    else if (tt < 2.0f) {
+                        const float t1 = FSUB(tt, 1.0f), t2 = FSUB(2.0f, tt);
+                        piece = FSUB(1.0f, FMUL(FADD(FMUL(t1, t1), FMUL(t2, t2)), 0.5f));
+                    } else {
+                        const float t3 = FSUB(3.0f, tt);
+                        piece = FMUL(FMUL(t3, t3), 0.5f);
+                    }
+                    weight = FMUL(weight, piece);
+                }
+                if (weight > 1e-6f) result = FADD(result, FMUL(weight, __ldg(t.N + e.y)));
+            }
+        }
+    }
+    if (store) out[s] = FMUL(result, post);
+}
+
 template <class C, bool FAST>
 __global__ void k_perlin(const int32_t *perm, C c, size_t first, size_t count, float *out)
 {
@@ -479,7 +623,15 @@ int wn_launch_proj_affine(WnTileView t, WnAffine c, const float nrm[3], size_t f
                           float *out, cudaStream_t st)
 {
     if (!count) return 0;
-    k_proj<WnAffine><<<blocks_for(count, 128), 128, 0, st>>>(t, c, nullptr, nrm[0], nrm[1], nrm[2], first, count, post, out);
+    bool per_lane = false;                                     // WN_PROJ_WARP=0: every lane on its own (A/B runs, tests)
+    if (const char *e = getenv("WN_PROJ_WARP")) per_lane = atoi(e) == 0;
+    if (per_lane) k_proj<WnAffine><<<blocks_for(count, 128), 128, 0, st>>>(t, c, nullptr, nrm[0], nrm[1], nrm[2], first, count, post, out);
+    else {
+        // one warp per 8 x 4 pixel patch over the image rows the sample window [first, first + count) touches
+        const size_t row0 = first / (size_t)c.nu, row1 = (first + count - 1) / (size_t)c.nu;
+        const size_t patches = (size_t)((c.nu + 7) / 8) * ((row1 - row0) / 4 + 1);
+        k_proj_grid<<<(unsigned)((patches + 3) / 4), 128, 0, st>>>(t, c, nrm[0], nrm[1], nrm[2], first, count, post, out);
+    }
     return 1;
 }
 int wn_launch_perlin_points(const int32_t *perm, WnPointsAoS c, size_t first, size_t count, float *out, int fast, cudaStream_t st)
