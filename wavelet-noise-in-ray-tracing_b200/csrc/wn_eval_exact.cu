@@ -349,7 +349,7 @@ constexpr int PROJ_LIST = 192;                                 // candidate cell
 __global__ void __launch_bounds__(128, 8) k_proj_grid(WnTileView t, WnAffine c, float n0, float n1, float n2, size_t first,
                                                    size_t count, float post, float *out)
 {
-    __shared__ int2 s_list[4][PROJ_LIST];                      // {cell relative to the union box (4 bits per axis... 5), tile index}
+    __shared__ float4 s_list[4][PROJ_LIST];                    // {cell x, y, z as floats, tile index (int bits)}
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // a warp owns an 8 x 4 patch of pixels (not 32 pixels of one row): its points are closer together, so the union of
@@ -421,9 +421,12 @@ __global__ void __launch_bounds__(128, 8) k_proj_grid(WnTileView t, WnAffine c, 
                 bound[i] = 1.5f + sl + eps;
             }
             listed = 0;
+            // idx -> (x, y, z) by float reciprocals: exact for these small integers (idx < 8192 + 32, divisors <= 1024)
+            const float inv01 = 1.0f / (float)(e0 * e1), inv0 = 1.0f / (float)e0;
             for (int base = 0; base < total; base += 32) {
                 const int idx = base + lane;
-                const int z = idx / (e0 * e1), r = idx - z * (e0 * e1), y = r / e0, x = r - y * e0;
+                const int z = (int)(((float)idx + 0.5f) * inv01), r = idx - z * (e0 * e1);
+                const int y = (int)(((float)r + 0.5f) * inv0), x = r - y * e0;
                 const float d0 = (float)(ulo[0] + x) - pc[0], d1 = (float)(ulo[1] + y) - pc[1], d2 = (float)(ulo[2] + z) - pc[2];
                 const float m = 0.5f * (nrm[0] * d0 + nrm[1] * d1 + nrm[2] * d2);
                 const bool keep = idx < total && fabsf(d0 - nrm[0] * m) < bound[0] && fabsf(d1 - nrm[1] * m) < bound[1] &&
@@ -431,8 +434,9 @@ __global__ void __launch_bounds__(128, 8) k_proj_grid(WnTileView t, WnAffine c, 
                 const unsigned km = __ballot_sync(full, keep);
                 const int pos = listed + __popc(km & ((1u << lane) - 1u));
                 if (keep && pos < PROJ_LIST)
-                    s_list[warp][pos] = make_int2(x | (y << 5) | (z << 10),
-                                                  tmod(ulo[0] + x, t) + tmod(ulo[1] + y, t) * t.n + tmod(ulo[2] + z, t) * t.n * t.n);
+                    s_list[warp][pos] = make_float4((float)(ulo[0] + x), (float)(ulo[1] + y), (float)(ulo[2] + z),
+                                                    __int_as_float(tmod(ulo[0] + x, t) + tmod(ulo[1] + y, t) * t.n +
+                                                                   tmod(ulo[2] + z, t) * t.n * t.n));
                 listed += __popc(km);
             }
             __syncwarp();
@@ -441,36 +445,42 @@ __global__ void __launch_bounds__(128, 8) k_proj_grid(WnTileView t, WnAffine c, 
             if (live) result = eval3d_projected(t, p, nrm);   // incoherent warp (not an image grid after all)
         } else if (live) {
             const float q0 = FSUB(p[0], 1.5f), q1 = FSUB(p[1], 1.5f), q2 = FSUB(p[2], 1.5f);
-            for (int k = 0; k < listed; ++k) {
-                const int2 e = s_list[warp][k];
-                const int c0 = ulo[0] + (e.x & 31), c1 = ulo[1] + ((e.x >> 5) & 31), c2 = ulo[2] + (e.x >> 10);
-                // the reference only visits its own box (cpp:235-237)
-                if (!samebox && (c0 < lo[0] || c0 > hi[0] || c1 < lo[1] || c1 > hi[1] || c2 < lo[2] || c2 > hi[2])) continue;
-                const float f0 = (float)c0, f1 = (float)c1, f2 = (float)c2;
+            const float flo[3] = { (float)lo[0], (float)lo[1], (float)lo[2] }, fhi[3] = { (float)hi[0], (float)hi[1], (float)hi[2] };
+            // one candidate cell, evaluated exactly like the reference's inner statement (cpp:239-260)
+            auto cell = [&](const float4 e, bool ok) {
+                const float fc[3] = { e.x, e.y, e.z };
                 // dot = ((0 + n0 (p0-c0)) + n1 (p1-c1)) + n2 (p2-c2), cpp:239-240
-                float dot = FADD(0.0f, FMUL(nrm[0], FSUB(p[0], f0)));
-                dot = FADD(dot, FMUL(nrm[1], FSUB(p[1], f1)));
-                dot = FADD(dot, FMUL(nrm[2], FSUB(p[2], f2)));
-                float weight = 1.0f;
-                const float fc[3] = { f0, f1, f2 };
+                float dot = FADD(0.0f, FMUL(nrm[0], FSUB(p[0], fc[0])));
+                dot = FADD(dot, FMUL(nrm[1], FSUB(p[1], fc[1])));
+                dot = FADD(dot, FMUL(nrm[2], FSUB(p[2], fc[2])));
                 const float qq[3] = { q0, q1, q2 };
+                // The reference stops at the first axis whose t leaves (0, 3) and skips the cell (cpp:247-250); here all
+                // three axes are evaluated without branches and the cell is skipped through `ok`: the same cells
+                // contribute, with the same weight ((1 * piece0) * piece1) * piece2 (1 * x is x exactly).
+                float weight = 0.0f;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     // t = (c_i + n_i*dot/2) - (p_i - 1.5), cpp:245
                     const float tt = FSUB(FADD(fc[i], FMUL(FMUL(nrm[i], dot), 0.5f)), qq[i]);
-                    if (tt <= 0.0f || tt >= 3.0f) { weight = 0.0f; break; }
-                    float piece;
-                    if (tt < 1.0f) piece = FMUL(FMUL(tt, tt), 0.5f);
-                    else if (tt < 2.0f) {
-                        const float t1 = FSUB(tt, 1.0f), t2 = FSUB(2.0f, tt);
-                        piece = FSUB(1.0f, FMUL(FADD(FMUL(t1, t1), FMUL(t2, t2)), 0.5f));
-                    } else {
-                        const float t3 = FSUB(3.0f, tt);
-                        piece = FMUL(FMUL(t3, t3), 0.5f);
-                    }
-                    weight = FMUL(weight, piece);
+                    ok = ok && tt > 0.0f && tt < 3.0f;
+                    const float edge = tt < 1.0f ? tt : FSUB(3.0f, tt);                      // t^2/2 or (3-t)^2/2
+                    const float pe = FMUL(FMUL(edge, edge), 0.5f);
+                    const float t1 = FSUB(tt, 1.0f), t2 = FSUB(2.0f, tt);
+                    const float pm = FSUB(1.0f, FMUL(FADD(FMUL(t1, t1), FMUL(t2, t2)), 0.5f));
+                    const float piece = (tt >= 1.0f && tt < 2.0f) ? pm : pe;
+                    weight = i == 0 ? piece : FMUL(weight, piece);
                 }
-                if (weight > 1e-6f) result = FADD(result, FMUL(weight, __ldg(t.N + e.y)));
+                if (ok && weight > 1e-6f) result = FADD(result, FMUL(weight, __ldg(t.N + __float_as_int(e.w))));
+            };
+            if (samebox) {
+#pragma unroll 2
+                for (int k = 0; k < listed; ++k) cell(s_list[warp][k], true);
+            } else {
+                for (int k = 0; k < listed; ++k) {
+                    const float4 e = s_list[warp][k];
+                    // the reference only visits its own box (cpp:235-237)
+                    cell(e, e.x >= flo[0] && e.x <= fhi[0] && e.y >= flo[1] && e.y <= fhi[1] && e.z >= flo[2] && e.z <= fhi[2]);
+                }
             }
         }
     }
