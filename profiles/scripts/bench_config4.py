@@ -52,6 +52,10 @@ ms_proj = timed(lambda: noise.evaluate3DProjected_grid(origin, e1, ax, e2, ax, n
 proj = out.cpu().numpy().copy()
 ms_perl = timed(lambda: perlin.noise_grid(origin, e1, ax, e2, ax, float(pre_p), out=out))
 perl = out.cpu().numpy().copy()
+perlin.set_precision(wn.WN_PERLIN_F32)                        # opt-in FP32 mode of the Perlin kernel
+ms_perl32 = timed(lambda: perlin.noise_grid(origin, e1, ax, e2, ax, float(pre_p), out=out))
+perl32_err = float(np.abs(out.cpu().numpy() - perl).max())
+perlin.set_precision(wn.WN_PERLIN_F64)
 ms_plain = timed(lambda: noise.evaluate3D_grid(origin, e1, ax, e2, ax, float(pre_w), 1.0, out=out))
 
 orc = Oracle()
@@ -72,6 +76,7 @@ print(json.dumps({
     "config": f"BASELINE config 4, {S}x{S} plane, normal (1,2,3)/sqrt14", "samples": n,
     "projected_ms": ms_proj, "projected_gsamples_s": n / ms_proj / 1e6,
     "perlin_fp64_ms": ms_perl, "perlin_gsamples_s": n / ms_perl / 1e6,
+    "perlin_fp32_ms": ms_perl32, "perlin_fp32_gsamples_s": n / ms_perl32 / 1e6, "perlin_fp32_max_abs_diff_to_fp64": perl32_err,
     "evaluate3d_grid_exact_ms": ms_plain, "evaluate3d_grid_gsamples_s": n / ms_plain / 1e6,
     "bit_exact_vs_oracle_65536_pixels": {"projected": ok_proj, "perlin": ok_perl},
     "cpu_oracle_msamples_s": {"projected": (1 << 16) / cpu_proj_s / 1e6, "perlin": (1 << 16) / cpu_perl_s / 1e6,
