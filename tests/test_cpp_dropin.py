@@ -78,6 +78,10 @@ def test_cpp_scalar_surface_matches_oracle(oracle):
     assert f("copy_eval3d") == f("eval3d")
     assert f("proj") == oracle.eval3d_projected(tile, 128, p, [.6, 0, .8])
     assert f("coeff0") == tile[0] and f("coeff_last") == tile[-1]
+    ta, tb = oracle.generate_tile(16, 1, 3), oracle.generate_tile(16, 2, 3)
+    assert f("assign_before") == oracle.eval3d(ta, 16, p)
+    assert f("assign_after") == f("assign_source") == oracle.eval3d(tb, 16, p) and f("assign_coeff0") == tb[0]
+    assert f("assign_before") != f("assign_after")
     g = oracle.rng(7)
     oracle.generate_tile(16, 7, 2, g)
     t2 = oracle.generate_tile(16, 7, 2, g)

@@ -30,6 +30,16 @@ int main()
         line("coeff_last", n3.getNoiseCoefficients().back());
         WaveletNoise copy = n3;                      // implicit copy: must evaluate identically (lazy re-upload)
         line("copy_eval3d", copy.evaluate3D(p));
+        // copy ASSIGNMENT between two generated objects of the same size reuses the target's vector storage (same
+        // pointer, same size): the device tile must still follow the new coefficients (content fingerprint)
+        WaveletNoise a(16, 1), b(16, 2);
+        a.generateNoiseTile3D();
+        b.generateNoiseTile3D();
+        line("assign_before", a.evaluate3D(p));
+        a = b;
+        line("assign_after", a.evaluate3D(p));
+        line("assign_source", b.evaluate3D(p));
+        line("assign_coeff0", a.getNoiseCoefficients()[0]);
         WaveletNoise n2(16, 7);
         n2.generateNoiseTile2D();
         n2.generateNoiseTile2D();                    // second call continues the RNG stream
