@@ -266,6 +266,9 @@ typedef struct wn_gtile wn_gtile;
 #define WN_SHARD_SLAB    0   /* contiguous z-slabs / row-bands                                             */
 #define WN_SHARD_CYCLIC  1   /* volumes: 32-slice chunks dealt round-robin (every rank keeps the periodic
                                 structure of the whole volume, so per-rank work stays 1/N) */
+/* Host-only (no GPU needed): the slices / rows rank `rank` of `world` owns under `sharding`, ascending; *count = how
+ * many (may exceed capacity). */
+int  wn_debug_shard_indices(int total, int rank, int world, int sharding, int *indices, int capacity, int *count);
 int  wn_group_create(int ngpus /* <= 0: all visible */, const int *devices /* NULL: 0..ngpus-1 */, wn_group **out);
 int  wn_group_destroy(wn_group *g);
 int  wn_group_size(const wn_group *g);

@@ -175,6 +175,35 @@ def test_export_json_writes_the_viewer_files(golden_dir, tmp_path):
             assert got["data"] == want["data"], name
 
 
+def test_group_sharding_matches_the_python_partition():
+    """The C ABI's device groups cut volumes and images exactly like sharding.py (the process-per-GPU path): every
+    unit is owned by exactly one rank, block-cyclic = 32-slice chunks dealt round-robin, slabs = contiguous with the
+    remainder on the lowest ranks.  Host-only, no GPU."""
+    import ctypes as C
+    import numpy as np
+    wn = wnpkg.load()
+    sh = wnpkg.load_sub("sharding")
+    lib = wn._lib.lib
+    for total in (0, 1, 31, 32, 33, 128, 1000, 1024, 8192):
+        for world in (1, 2, 3, 4, 8):
+            seen = np.zeros(total, np.int32)
+            for rank in range(world):
+                for sharding in (wn.WN_SHARD_SLAB, wn.WN_SHARD_CYCLIC):
+                    buf = np.empty(max(total, 1), np.int32)
+                    n = C.c_int()
+                    wn._lib.check(lib.wn_debug_shard_indices(total, rank, world, sharding,
+                                                             buf.ctypes.data_as(C.POINTER(C.c_int32)), buf.size, C.byref(n)))
+                    got = buf[:n.value]
+                    if sharding == wn.WN_SHARD_CYCLIC:
+                        want = sh.cyclic_slab_indices(total, rank, world)
+                        seen[got] += 1
+                    else:
+                        b, e = sh.slab_range(total, rank, world)
+                        want = np.arange(b, e)
+                    assert np.array_equal(got, want), (total, world, rank, sharding)
+            assert (seen == 1).all()
+
+
 def test_bench_helpers():
     import importlib.util
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))

@@ -87,6 +87,7 @@ SIGNATURES = {
     "wn_wavelet_texture2d_values": (C.c_int, [vp, vp, C.c_size_t, C.c_double, C.c_int, vp, C.c_int]),
     "wn_perlin_texture_values": (C.c_int, [vp, vp, C.c_size_t, C.c_double, C.c_int, vp, C.c_int]),
     "wn_stats_compute": (C.c_int, [vp, vp, C.c_size_t, C.c_int, C.POINTER(WnStats)]),
+    "wn_debug_shard_indices": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int, C.POINTER(C.c_int)]),
     "wn_group_create": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
     "wn_group_destroy": (C.c_int, [vp]),
     "wn_group_size": (C.c_int, [vp]),

@@ -221,6 +221,17 @@ int finish(wn_group *g, float *ms)
 
 }  // namespace
 
+// host-only: the z indices (or rows) rank `rank` of `world` owns under `sharding` -- what the sharded calls use
+extern "C" int wn_debug_shard_indices(int total, int rank, int world, int sharding, int *indices, int capacity, int *count)
+{
+    WG_REQUIRE(count && total >= 0 && world > 0 && rank >= 0 && rank < world, "wn_debug_shard_indices: bad argument");
+    WG_REQUIRE(sharding == WN_SHARD_SLAB || sharding == WN_SHARD_CYCLIC, "bad sharding %d", sharding);
+    const std::vector<int> idx = shard_indices(total, rank, world, sharding);
+    *count = (int)idx.size();
+    for (int i = 0; i < (int)idx.size() && i < capacity && indices; ++i) indices[i] = idx[i];
+    return WN_OK;
+}
+
 extern "C" int wn_group_create(int ngpus, const int *devices, wn_group **out)
 {
     WG_REQUIRE(out, "wn_group_create: out is NULL");
