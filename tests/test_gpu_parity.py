@@ -592,7 +592,8 @@ def test_replica_kernel_variants_are_bit_identical(wn, oracle, gpu_tiles, tiles1
     ]
     variants = [{"WN_REP": "0"}, {}, {"WN_REP_TMA": "0"}, {"WN_REP": "12"}, {"WN_REP": "11"}, {"WN_REP_SHARE": "0"},
                 {"WN_REP": "12", "WN_REP_YPW": "4"}, {"WN_FOLD_BUDGET": str(1 << 27), "WN_REP_TMA": "1"},
-                {"WN_FOLD_BUDGET": str(1 << 27), "WN_REP": "22", "WN_REP_TMA": "0"}]
+                {"WN_FOLD_BUDGET": str(1 << 27), "WN_REP": "22", "WN_REP_TMA": "0"},
+                {"WN_REP_BY": "16"}, {"WN_REP_BY": "16", "WN_REP": "12"}, {"WN_REP_BY": "16", "WN_REP_SHARE": "0"}]
     for ci, (xs, ys, zs, bs, ws) in enumerate(cases):
         base = None
         for env in variants:

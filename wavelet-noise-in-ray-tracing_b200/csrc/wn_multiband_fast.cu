@@ -968,13 +968,14 @@ constexpr int rep_min_blocks(int windows) { return windows <= 2 ? 3 : 2; }
 
 // NB direct bands; the last NSH of them are shared by the replicas (see q4_footprints_rep), the others have one window
 // per replica
-template <int NB, int NSH, int RX, int RY, int YPW, int RINGMODE, bool POW2>
-__global__ void __launch_bounds__(256, rep_min_blocks((NB - NSH) * RX * RY + NSH))
+template <int NB, int NSH, int RX, int RY, int YPW, int RINGMODE, int BY, bool POW2>
+__global__ void __launch_bounds__(32 * BY, BY == 8 ? rep_min_blocks((NB - NSH) * RX * RY + NSH) : 1)
 k_mb3d_rep(const float *__restrict__ N, int n, WnTabs tabs, int nx, int ny, int nk, int max_rows, WnFold fold,
            WnOrder ord, WnRep rep, const __grid_constant__ CUtensorMap pmap, float *__restrict__ out)
 {
-    constexpr int BX = 128, BY = 8, BZ = 32, NT = 256, R = RX * RY;
-    constexpr int RING = NB == 1 ? 8 : 4;                       // period-block planes in flight (two bands: U needs the room)
+    constexpr int BX = 128, BZ = 32, NT = 32 * BY, R = RX * RY;
+    // period-block planes in flight (two bands in 8-row bricks: U needs the room for two CTAs per SM)
+    constexpr int RING = (NB == 1 || BY == 16) ? 8 : 4;
     constexpr int HP = RING / 2;                                // RINGMODE 1: planes per TMA box = half a ring
     constexpr int PER_BAND = BX + BY + BZ;
     constexpr int LPR = 32 / YPW;                               // lanes per y row of a warp
@@ -1483,8 +1484,8 @@ bool axis_replica_shift(const HostEntry *e, const int *first, int len, int *shif
     return true;
 }
 
-// tensor map of the period block float32[Lz][Ly][Lx] with a 128 x 8 x planes box (one half of the kernel's ring)
-bool make_period_map(const float *P, int Lx, int Ly, int Lz, int planes, CUtensorMap *map)
+// tensor map of the period block float32[Lz][Ly][Lx] with a 128 x by x planes box (one half of the kernel's ring)
+bool make_period_map(const float *P, int Lx, int Ly, int Lz, int by, int planes, CUtensorMap *map)
 {
     typedef CUresult (*Encode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1502,18 +1503,19 @@ bool make_period_map(const float *P, int Lx, int Ly, int Lz, int planes, CUtenso
     if (!encode) return false;
     const cuuint64_t dims[3] = { (cuuint64_t)Lx, (cuuint64_t)Ly, (cuuint64_t)Lz };
     const cuuint64_t strides[2] = { (cuuint64_t)Lx * sizeof(float), (cuuint64_t)Lx * Ly * sizeof(float) };
-    const cuuint32_t box[3] = { 128, 8, (cuuint32_t)planes }, estr[3] = { 1, 1, 1 };
+    const cuuint32_t box[3] = { 128, (cuuint32_t)by, (cuuint32_t)planes }, estr[3] = { 1, 1, 1 };
     return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(P), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int NB, int NSH, int RX, int RY, int YPW, int RINGMODE>
+template <int NB, int NSH, int RX, int RY, int YPW, int RINGMODE, int BY>
 int launch_rep(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk, float *out, int max_rows, size_t smem, WnFold fold,
                const WnRep &rep, const CUtensorMap &pmap, cudaStream_t st)
 {
-    constexpr int BY = 8, BZ = 32, NT = 256;
-    auto kern = t.pow2 ? k_mb3d_rep<NB, NSH, RX, RY, YPW, RINGMODE, true> : k_mb3d_rep<NB, NSH, RX, RY, YPW, RINGMODE, false>;
+    constexpr int BZ = 32, NT = 32 * BY;
+    auto kern = t.pow2 ? k_mb3d_rep<NB, NSH, RX, RY, YPW, RINGMODE, BY, true>
+                       : k_mb3d_rep<NB, NSH, RX, RY, YPW, RINGMODE, BY, false>;
     if (!allow_smem(kern, smem)) return -1;
     const int nyb = (rep.by + BY - 1) / BY, nzb = (nk + BZ - 1) / BZ;
     WnOrder ord{1, nyb, 1, nzb};
@@ -1533,7 +1535,10 @@ int launch_rep(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk, float *
 // Replica kernel for a lattice window with one or two direct bands.  Returns kernels launched, 0 when the window does
 // not qualify (the caller falls back to k_mb3d_col4), -1 on a launch error.
 // Knobs (A/B runs): WN_REP=0 off, "11" / "12" / "22" = at most that many replicas along x and y (default "22");
-// WN_REP_YPW=1|4 thread mapping (NB = 1 only); WN_REP_TMA=0|1 period-block ring; WN_REP_SHARE=0: no shared bands.
+// WN_REP_YPW=1|4 thread mapping (NB = 1 only); WN_REP_TMA=0|1 period-block ring; WN_REP_SHARE=0: no shared bands;
+// WN_REP_BY=16: 128 x 16 x 32 bricks, 512 threads, one CTA per SM with an 8-plane ring (measured 0.843 ms against
+// 0.830 ms for the default two 8-row CTAs per SM on config 3: fewer X-pass rows, but the prologue is no longer hidden
+// behind a second CTA).
 int rep_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsigned char *rows, int k0, int nx, int ny, int nk,
              const WnBands &b, WnFold fold, float *out, cudaStream_t st)
 {
@@ -1552,10 +1557,10 @@ int rep_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsigned
     bool ok_y = want_ry == 2 && ny % 2 == 0 && (!fold.P || (ny / 2) % fold.Ly == 0);
     for (int i = 0; i < nb && ok_x; ++i) ok_x = axis_replica_shift(h.ex(rows[i]), h.fx(rows[i]), nx, &cxs[i]);
     for (int i = 0; i < nb && ok_y; ++i) ok_y = axis_replica_shift(h.ey(rows[i]), h.fy(rows[i]), ny, &cys[i]);
-    const int ring_planes = nb == 1 ? 8 : 4;                   // RING of k_mb3d_rep
-    const size_t ring_bytes = fold.P ? (size_t)ring_planes * 256 * sizeof(float4) : 0;
+    int want_by = 8;                                           // brick rows (= warps per CTA); 16: one CTA per SM
+    if (const char *e = getenv("WN_REP_BY")) want_by = atoi(e) == 16 ? 16 : 8;
     // candidates in order of preference; the first one whose windows fit the registers and whose U rows leave room for
-    // two CTAs per SM (<= ~113 KB each) is used
+    // two CTAs per SM (<= ~113 KB each; 16-row bricks: one CTA, <= ~226 KB) is used
     const int cand[3][2] = { {2, 2}, {1, 2}, {1, 1} };
     for (int ci = 0; ci < 3; ++ci) {
         const int RX = cand[ci][0], RY = cand[ci][1], R = RX * RY;
@@ -1571,33 +1576,43 @@ int rep_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsigned
             }
         const int windows = (nb - nsh) * R + nsh;
         if (windows > (nsh ? 5 : 4)) continue;
+        int ypw = 1, tma = 1;
+        if (const char *e = getenv("WN_REP_YPW")) ypw = (atoi(e) == 4 && nb == 1) ? 4 : 1;
+        if (const char *e = getenv("WN_REP_TMA")) tma = atoi(e) != 0;
+        // the 16-row brick exists for the TMA ring only; anything else runs the 8-row kernel
+        const bool tma_ok16 = tma && ypw == 1 && fold.P && fold.Lx % 128 == 0 && fold.Ly % 16 == 0 && fold.Lz % 4 == 0 &&
+                              fold.kphase % 4 == 0 && rep.bx % 128 == 0 && rep.by % 16 == 0 && nk % 32 == 0;
+        const int by = (want_by == 16 && tma_ok16) ? 16 : 8;
+        const int ring_planes = (nb == 1 || by == 16) ? 8 : 4;     // RING of k_mb3d_rep
+        const size_t ring_bytes = fold.P ? (size_t)ring_planes * 32 * by * sizeof(float4) : 0;
         int max_rows = 0;
         bool ok = true;
         for (int i = 0; i < nb && ok; ++i) {
-            const BrickPlan pb = plan_bricks(h, rows + i, 1, rep.by, k0, nk, 8, 32, 128, true);
+            const BrickPlan pb = plan_bricks(h, rows + i, 1, rep.by, k0, nk, by, 32, 128, true);
             ok = pb.ok;
             max_rows += pb.max_rows * (i < nb - nsh ? R : 1);
         }
         if (!ok) return 0;                                     // unsorted axes / huge footprints: not a brick lattice
         const size_t smem = ring_bytes + (size_t)max_rows * (128 * sizeof(float) + sizeof(int)) +
-                            (size_t)nb * (128 + 8 + 32) * sizeof(float4) + 64;
-        if (smem > 113 * 1024) continue;
-        int ypw = 1, tma = 1;
-        if (const char *e = getenv("WN_REP_YPW")) ypw = (atoi(e) == 4 && nb == 1) ? 4 : 1;
-        if (const char *e = getenv("WN_REP_TMA")) tma = atoi(e) != 0;
+                            (size_t)nb * (128 + by + 32) * sizeof(float4) + 64;
+        if (smem > (size_t)(by == 8 ? 113 : 226) * 1024) continue;
         CUtensorMap pmap;
         std::memset(&pmap, 0, sizeof(pmap));
-        tma = tma && fold.P && fold.Lx % 128 == 0 && fold.Ly % 8 == 0 && fold.Lz % 4 == 0 && fold.kphase % 4 == 0 &&
-              rep.bx % 128 == 0 && rep.by % 8 == 0 && nk % 32 == 0 &&
-              make_period_map(fold.P, fold.Lx, fold.Ly, fold.Lz, ring_planes / 2, &pmap);
+        tma = tma && fold.P && fold.Lx % 128 == 0 && fold.Ly % by == 0 && fold.Lz % 4 == 0 && fold.kphase % 4 == 0 &&
+              rep.bx % 128 == 0 && rep.by % by == 0 && nk % 32 == 0 &&
+              make_period_map(fold.P, fold.Lx, fold.Ly, fold.Lz, by, ring_planes / 2, &pmap);
+        if (by == 16 && !tma) return -1;                       // the driver entry point vanished between two calls
         for (int r = 0; r < 4; ++r)
             rep.roff[r] = 4LL * ((long long)(r % RX) * rep.bx + (long long)nx * ((long long)(r / RX) * rep.by));
-#define WN_REP_CASE(NB_, NSH_, RX_, RY_, YPW_, TMA_)                                                                     \
-        if (nb == NB_ && nsh == NSH_ && RX == RX_ && RY == RY_ && ypw == YPW_ && tma == TMA_)                           \
-            return launch_rep<NB_, NSH_, RX_, RY_, YPW_, TMA_>(t, tabs, nx, ny, nk, out, max_rows, smem, fold, rep, pmap, st);
-#define WN_REP_CASES(NB_, NSH_, RX_, RY_) WN_REP_CASE(NB_, NSH_, RX_, RY_, 1, 1) WN_REP_CASE(NB_, NSH_, RX_, RY_, 1, 0)
+#define WN_REP_CASE(NB_, NSH_, RX_, RY_, YPW_, TMA_, BY_)                                                                \
+        if (nb == NB_ && nsh == NSH_ && RX == RX_ && RY == RY_ && ypw == YPW_ && tma == TMA_ && by == BY_)              \
+            return launch_rep<NB_, NSH_, RX_, RY_, YPW_, TMA_, BY_>(t, tabs, nx, ny, nk, out, max_rows, smem, fold, rep,   \
+                                                                     pmap, st);
+#define WN_REP_CASES(NB_, NSH_, RX_, RY_)                                                                               \
+        WN_REP_CASE(NB_, NSH_, RX_, RY_, 1, 1, 8) WN_REP_CASE(NB_, NSH_, RX_, RY_, 1, 0, 8)                             \
+        WN_REP_CASE(NB_, NSH_, RX_, RY_, 1, 1, 16)
         WN_REP_CASES(1, 0, 1, 1) WN_REP_CASES(1, 0, 1, 2) WN_REP_CASES(1, 0, 2, 2)
-        WN_REP_CASE(1, 0, 1, 2, 4, 1) WN_REP_CASE(1, 0, 1, 2, 4, 0)
+        WN_REP_CASE(1, 0, 1, 2, 4, 1, 8) WN_REP_CASE(1, 0, 1, 2, 4, 0, 8)
         WN_REP_CASES(2, 0, 1, 1) WN_REP_CASES(2, 0, 1, 2)
         WN_REP_CASES(2, 1, 1, 2) WN_REP_CASES(2, 1, 2, 2)
 #undef WN_REP_CASES
