@@ -17,7 +17,7 @@ sh = importlib.import_module("wavelet-noise-in-ray-tracing_b200.sharding")
 
 nz = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-KNOBS = ("WN_REP", "WN_REP_YPW", "WN_REP_TMA", "WN_REP_SHARE", "WN_FOLD_BUDGET", "WN_REPLICA_ORDER", "WN_COL4", "WN_REP_BY")
+KNOBS = ("WN_REP", "WN_REP_YPW", "WN_REP_TMA", "WN_REP_SHARE", "WN_FOLD_BUDGET", "WN_REPLICA_ORDER", "WN_COL4", "WN_REP_BY", "WN_BRICK_FALLBACK")
 B24 = str(1 << 24)
 VARIANTS = [
     ("col4 (round 1), 512^3 block", {"WN_REP": "0"}),
@@ -35,6 +35,8 @@ for budget_name, budget in (("512^3", None), ("256^3", B24)):
                 VARIANTS.append((f"rep {rep} {'tma' if tma == '1' else 'cp.async'} share {share} {budget_name} block", env))
 VARIANTS.append(("default plan, 8-row bricks", {}))
 VARIANTS.append(("default plan, 16-row bricks", {"WN_REP_BY": "16"}))
+for idx in range(10):
+    VARIANTS.append((f"chain shape {idx}", {"WN_BRICK_FALLBACK": str(idx)}))
 if os.environ.get("TUNE_ONLY"):
     keep = os.environ["TUNE_ONLY"].split(",")
     VARIANTS = [v for i, v in enumerate(VARIANTS) if i < 2 or any(k in v[0] for k in keep)]

@@ -349,9 +349,16 @@ constexpr int PROJ_LIST = 192;                                 // candidate cell
 __global__ void __launch_bounds__(128, 8) k_proj_grid(WnTileView t, WnAffine c, float n0, float n1, float n2, size_t first,
                                                    size_t count, float post, float *out)
 {
-    __shared__ float4 s_list[4][PROJ_LIST];                    // {cell x, y, z as floats, tile index (int bits)}
+    // candidate cells in pairs: {x_a, x_b, y_a, y_b}, {z_a, z_b, tile index a, b (int bits)} -- cell coordinates as floats,
+    // laid out so that two LDS.128 deliver the operand pairs of the packed evaluation below
+    __shared__ float4 s_list[4][PROJ_LIST];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *const my_list = reinterpret_cast<float *>(s_list[warp]);
+    auto entry = [&](int k) {                                  // cell k of this warp's list as {x, y, z, index}
+        const float *q = my_list + (k >> 1) * 8 + (k & 1);
+        return make_float4(q[0], q[2], q[4], q[6]);
+    };
     // a warp owns an 8 x 4 patch of pixels (not 32 pixels of one row): its points are closer together, so the union of
     // their candidate cells is smaller (about 1.15x a single point's instead of 1.6x)
     const size_t row0 = first / (size_t)c.nu;                  // first image row of this launch's sample window
@@ -405,9 +412,19 @@ __global__ void __launch_bounds__(128, 8) k_proj_grid(WnTileView t, WnAffine c, 
         }
         const int e0 = uhi[0] - ulo[0] + 1, e1 = uhi[1] - ulo[1] + 1, e2 = uhi[2] - ulo[2] + 1;
         const int total = e0 * e1 * e2;
-        // every live lane has the union box as its own box (the usual case): no per-candidate box test needed
-        const bool samebox = __all_sync(full, !live || (lo[0] == ulo[0] && hi[0] == uhi[0] && lo[1] == ulo[1] && hi[1] == uhi[1] &&
-                                                         lo[2] == ulo[2] && hi[2] == uhi[2]));
+        // A lane's own box (the only cells the reference visits, cpp:235-237) is the union box minus, per face, at most
+        // one layer of cells when the warp's points are less than a cell apart: `excl` has bit 2i / 2i+1 set when the
+        // lane's box starts one cell after / ends one cell before the union's on axis i, and a listed cell carries the
+        // faces of the union box it lies on in bits 24..29 of its tile index, so "inside my box" is one AND.
+        unsigned excl = 0;
+        bool near = true;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            excl |= (lo[i] > ulo[i] ? 1u : 0u) << (2 * i) | (hi[i] < uhi[i] ? 1u : 0u) << (2 * i + 1);
+            near = near && lo[i] - ulo[i] <= 1 && uhi[i] - hi[i] <= 1;
+        }
+        excl <<= 24;
+        const bool nearbox = __all_sync(full, !live || near) && (long long)t.n * t.n * t.n <= (1LL << 24);
         int listed = PROJ_LIST + 1;                            // > PROJ_LIST: fall back to the per-lane walk
         if (e0 <= 32 && e1 <= 32 && e2 <= 32 && total <= 8192) {
             // |A (c - p)|_i < 1.5 for some lane  =>  |A (c - pc)|_i < 1.5 + sum_j |A_ij| hw_j (+ rounding slack)
@@ -433,11 +450,19 @@ __global__ void __launch_bounds__(128, 8) k_proj_grid(WnTileView t, WnAffine c, 
                                   fabsf(d2 - nrm[2] * m) < bound[2];
                 const unsigned km = __ballot_sync(full, keep);
                 const int pos = listed + __popc(km & ((1u << lane) - 1u));
-                if (keep && pos < PROJ_LIST)
-                    s_list[warp][pos] = make_float4((float)(ulo[0] + x), (float)(ulo[1] + y), (float)(ulo[2] + z),
-                                                    __int_as_float(tmod(ulo[0] + x, t) + tmod(ulo[1] + y, t) * t.n +
-                                                                   tmod(ulo[2] + z, t) * t.n * t.n));
+                if (keep && pos < PROJ_LIST) {
+                    float *q = my_list + (pos >> 1) * 8 + (pos & 1);
+                    q[0] = (float)(ulo[0] + x); q[2] = (float)(ulo[1] + y); q[4] = (float)(ulo[2] + z);
+                    const int faces = (x == 0) | (x == e0 - 1) << 1 | (y == 0) << 2 | (y == e1 - 1) << 3 | (z == 0) << 4 | (z == e2 - 1) << 5;
+                    q[6] = __int_as_float((tmod(ulo[0] + x, t) + tmod(ulo[1] + y, t) * t.n + tmod(ulo[2] + z, t) * t.n * t.n) |
+                                          (nearbox ? faces << 24 : 0));
+                }
                 listed += __popc(km);
+            }
+            __syncwarp();
+            if (lane < 4 && (listed & 1) && listed < PROJ_LIST) {  // odd count: the last pair's second cell repeats the first
+                float *q = my_list + (listed >> 1) * 8 + 2 * lane;
+                q[1] = q[0];
             }
             __syncwarp();
         }
@@ -472,12 +497,55 @@ __global__ void __launch_bounds__(128, 8) k_proj_grid(WnTileView t, WnAffine c, 
                 }
                 if (ok && weight > 1e-6f) result = FADD(result, FMUL(weight, __ldg(t.N + __float_as_int(e.w))));
             };
-            if (samebox) {
+            if (nearbox) {
+                // Two listed cells per iteration on the packed FP32 pipe: FADD2 / FMUL2 are the same IEEE operations as
+                // the scalar ones two at a time (a - b is formed as a + (-b), exact), so every cell keeps the reference's
+                // arithmetic; the two contributions are then added in list order.
+                // ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false, which the
+                // scalar .rn forms never are.  Where a sum takes a rounded product (the dot product, t1^2 + t2^2) the
+                // add is therefore done with two scalar FADDs (add2s); where the product is a multiplication by 0.5
+                // (exact: x/2 + y rounds like fl(x/2) + y) a contraction cannot change the result.
+                auto add2s = [](const float2 a, const float2 b) { return make_float2(FADD(a.x, b.x), FADD(a.y, b.y)); };
+                const float2 n2[3] = { make_float2(nrm[0], nrm[0]), make_float2(nrm[1], nrm[1]), make_float2(nrm[2], nrm[2]) };
+                const float2 p2[3] = { make_float2(p[0], p[0]), make_float2(p[1], p[1]), make_float2(p[2], p[2]) };
+                const float2 nq2[3] = { make_float2(-q0, -q0), make_float2(-q1, -q1), make_float2(-q2, -q2) };
+                const float2 half2 = make_float2(0.5f, 0.5f), one2 = make_float2(1.0f, 1.0f), two2 = make_float2(2.0f, 2.0f),
+                             three2 = make_float2(3.0f, 3.0f), mone2 = make_float2(-1.0f, -1.0f);
+                auto neg2 = [](const float2 a) { return make_float2(-a.x, -a.y); };
 #pragma unroll 2
-                for (int k = 0; k < listed; ++k) cell(s_list[warp][k], true);
+                for (int k = 0; k < listed; k += 2) {
+                    const float4 e01 = s_list[warp][k], e23 = s_list[warp][k + 1];
+                    const float2 fc[3] = { make_float2(e01.x, e01.y), make_float2(e01.z, e01.w), make_float2(e23.x, e23.y) };
+                    float2 dot = __fadd2_rn(make_float2(0.0f, 0.0f), __fmul2_rn(n2[0], __fadd2_rn(p2[0], neg2(fc[0]))));
+                    dot = add2s(dot, __fmul2_rn(n2[1], __fadd2_rn(p2[1], neg2(fc[1]))));
+                    dot = add2s(dot, __fmul2_rn(n2[2], __fadd2_rn(p2[2], neg2(fc[2]))));
+                    const unsigned wa = (unsigned)__float_as_int(e23.z), wb = (unsigned)__float_as_int(e23.w);
+                    bool oka = (wa & excl) == 0, okb = (wb & excl) == 0 && k + 1 < listed;
+                    float2 weight = make_float2(0.0f, 0.0f);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const float2 tt = __fadd2_rn(__fadd2_rn(fc[i], __fmul2_rn(__fmul2_rn(n2[i], dot), half2)), nq2[i]);
+                        // The reference's tests (0 < t < 3; t < 1, t < 2: cpp:247-256) through u = t - 1.5, which is
+                        // exact for t in [0.75, 3]: |u| < 1.5 drops, besides t <= 0 and t >= 3, only t < 2^-24 (piece
+                        // t^2/2 < 2^-49: the cell fails the 1e-6 weight test either way); |u| < 0.5 is 1 < t < 2, and
+                        // at t = 1 the edge polynomial t^2/2 and the middle one give the same 0.5.
+                        const float2 u = __fadd2_rn(tt, make_float2(-1.5f, -1.5f));
+                        oka = oka && fabsf(u.x) < 1.5f;
+                        okb = okb && fabsf(u.y) < 1.5f;
+                        const float2 t3 = __fadd2_rn(three2, neg2(tt));
+                        const float2 edge = make_float2(u.x < 0.0f ? tt.x : t3.x, u.y < 0.0f ? tt.y : t3.y);
+                        const float2 pe = __fmul2_rn(__fmul2_rn(edge, edge), half2);
+                        const float2 t1 = __fadd2_rn(tt, mone2), t2 = __fadd2_rn(two2, neg2(tt));
+                        const float2 pm = __fadd2_rn(one2, neg2(__fmul2_rn(add2s(__fmul2_rn(t1, t1), __fmul2_rn(t2, t2)), half2)));
+                        const float2 piece = make_float2(fabsf(u.x) < 0.5f ? pm.x : pe.x, fabsf(u.y) < 0.5f ? pm.y : pe.y);
+                        weight = i == 0 ? piece : __fmul2_rn(weight, piece);
+                    }
+                    if (oka && weight.x > 1e-6f) result = FADD(result, FMUL(weight.x, __ldg(t.N + (wa & 0xffffffu))));
+                    if (okb && weight.y > 1e-6f) result = FADD(result, FMUL(weight.y, __ldg(t.N + (wb & 0xffffffu))));
+                }
             } else {
                 for (int k = 0; k < listed; ++k) {
-                    const float4 e = s_list[warp][k];
+                    const float4 e = entry(k);
                     // the reference only visits its own box (cpp:235-237)
                     cell(e, e.x >= flo[0] && e.x <= fhi[0] && e.y >= flo[1] && e.y <= fhi[1] && e.z >= flo[2] && e.z <= fhi[2]);
                 }

@@ -1679,6 +1679,17 @@ int brick_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsign
         if (!plan.ok || plan.smem > 100 * 1024) pick = -1;
     }
     if (pick < 0) {
+        // WN_BRICK_FALLBACK=<index>: shape of the passes the streaming kernels above did not take (A/B runs)
+        if (const char *e = getenv("WN_BRICK_FALLBACK")) {
+            const int p = atoi(e);
+            if (p >= 0 && p < kNumShapes && (p < kFirstShape4 || can4)) {
+                plan = plan_bricks(h, rows, b.nbands, ny, k0, nk, kShapes[p].by, kShapes[p].bz, p >= kFirstShape4 ? 128 : 32,
+                                   p >= kFirstShape4);
+                if (plan.ok && plan.smem <= 100 * 1024) pick = p;
+            }
+        }
+    }
+    if (pick < 0) {
         if (can4) {
             pick = kFirstShape4;                               // 128 x 8 x 8 samples, small footprints only
             plan = plan_bricks(h, rows, b.nbands, ny, k0, nk, kShapes[pick].by, kShapes[pick].bz, 128, true);
