@@ -438,26 +438,63 @@ __global__ void __launch_bounds__(128, 8) k_proj_grid(WnTileView t, WnAffine c, 
                 bound[i] = 1.5f + sl + eps;
             }
             listed = 0;
-            // idx -> (x, y, z) by float reciprocals: exact for these small integers (idx < 8192 + 32, divisors <= 1024)
-            const float inv01 = 1.0f / (float)(e0 * e1), inv0 = 1.0f / (float)e0;
-            for (int base = 0; base < total; base += 32) {
-                const int idx = base + lane;
-                const int z = (int)(((float)idx + 0.5f) * inv01), r = idx - z * (e0 * e1);
-                const int y = (int)(((float)r + 0.5f) * inv0), x = r - y * e0;
-                const float d0 = (float)(ulo[0] + x) - pc[0], d1 = (float)(ulo[1] + y) - pc[1], d2 = (float)(ulo[2] + z) - pc[2];
-                const float m = 0.5f * (nrm[0] * d0 + nrm[1] * d1 + nrm[2] * d2);
-                const bool keep = idx < total && fabsf(d0 - nrm[0] * m) < bound[0] && fabsf(d1 - nrm[1] * m) < bound[1] &&
-                                  fabsf(d2 - nrm[2] * m) < bound[2];
-                const unsigned km = __ballot_sync(full, keep);
-                const int pos = listed + __popc(km & ((1u << lane) - 1u));
-                if (keep && pos < PROJ_LIST) {
-                    float *q = my_list + (pos >> 1) * 8 + (pos & 1);
-                    q[0] = (float)(ulo[0] + x); q[2] = (float)(ulo[1] + y); q[4] = (float)(ulo[2] + z);
-                    const int faces = (x == 0) | (x == e0 - 1) << 1 | (y == 0) << 2 | (y == e1 - 1) << 3 | (z == 0) << 4 | (z == e2 - 1) << 5;
-                    q[6] = __int_as_float((tmod(ulo[0] + x, t) + tmod(ulo[1] + y, t) * t.n + tmod(ulo[2] + z, t) * t.n * t.n) |
-                                          (nearbox ? faces << 24 : 0));
+            // One (y, z) row of the union box per lane.  (A d)_i is affine in d_0 = c_0 - pc_0 for a fixed row:
+            //   (A d)_0 = a0 d_0 + k0,  (A d)_1 = a1 d_0 + k1,  (A d)_2 = a2 d_0 + k2   (a0 = 1 - n0^2/2 in [0.5, 1]),
+            // so the cells of the row that can pass |(A d)_i| < bound_i form one interval of x; it is widened by eps again
+            // for the rounding of its own end points (a listed cell that does not contribute is only wasted work).  The
+            // rows' cell counts are scanned across the warp, so the list keeps the reference's visiting order.
+            const float a0 = 1.0f - 0.5f * nrm[0] * nrm[0], a1 = -0.5f * nrm[1] * nrm[0], a2 = -0.5f * nrm[2] * nrm[0];
+            const bool use1 = fabsf(a1) > 1e-6f, use2 = fabsf(a2) > 1e-6f;
+            const float ia0 = 1.0f / a0, ia1 = use1 ? 1.0f / a1 : 0.0f, ia2 = use2 ? 1.0f / a2 : 0.0f;
+            const int nrows = e1 * e2;
+            const float inv1 = 1.0f / (float)e1;               // row -> (y, z) by a float reciprocal: exact for rows < 2^10
+            for (int base = 0; base < nrows; base += 32) {
+                const int rr = base + lane;
+                const int z = (int)(((float)rr + 0.5f) * inv1), y = rr - z * e1;
+                int cnt = 0, xlo = 0;
+                if (rr < nrows) {
+                    const float d1 = (float)(ulo[1] + y) - pc[1], d2 = (float)(ulo[2] + z) - pc[2];
+                    const float mk = 0.5f * (nrm[1] * d1 + nrm[2] * d2);
+                    const float k0 = -nrm[0] * mk, k1 = d1 - nrm[1] * mk, k2 = d2 - nrm[2] * mk;
+                    float dlo = fmaxf((-bound[0] - k0) * ia0, -32.0f), dhi = fminf((bound[0] - k0) * ia0, 32.0f);
+                    bool empty = false;
+                    if (use1) {
+                        const float x0 = (-bound[1] - k1) * ia1, x1 = (bound[1] - k1) * ia1;
+                        dlo = fmaxf(dlo, fminf(x0, x1)); dhi = fminf(dhi, fmaxf(x0, x1));
+                    } else empty = fabsf(k1) >= bound[1] + 1.0e-4f;   // |a1 d_0| <= 1e-6 * 32
+                    if (use2) {
+                        const float x0 = (-bound[2] - k2) * ia2, x1 = (bound[2] - k2) * ia2;
+                        dlo = fmaxf(dlo, fminf(x0, x1)); dhi = fminf(dhi, fmaxf(x0, x1));
+                    } else empty = empty || fabsf(k2) >= bound[2] + 1.0e-4f;
+                    if (!empty && dlo <= dhi) {
+                        xlo = max(ulo[0], (int)ceilf(pc[0] + dlo - eps));
+                        cnt = max(0, min(uhi[0], (int)floorf(pc[0] + dhi + eps)) - xlo + 1);
+                    }
                 }
-                listed += __popc(km);
+                int inc = cnt;                                 // inclusive scan of the rows' counts
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(full, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                const int start = listed + inc - cnt;
+                listed += __shfl_sync(full, inc, 31);
+                if (cnt > 0) {
+                    const float fy = (float)(ulo[1] + y), fz = (float)(ulo[2] + z);
+                    const int iyz = tmod(ulo[1] + y, t) * t.n + tmod(ulo[2] + z, t) * t.n * t.n;
+                    const int faces_yz = nearbox ? ((y == 0) << 2 | (y == e1 - 1) << 3 | (z == 0) << 4 | (z == e2 - 1) << 5) << 24 : 0;
+                    int ix = tmod(xlo, t);
+                    for (int j = 0; j < cnt; ++j) {
+                        const int pos = start + j, x = xlo + j;
+                        if (pos < PROJ_LIST) {
+                            float *q = my_list + (pos >> 1) * 8 + (pos & 1);
+                            q[0] = (float)x; q[2] = fy; q[4] = fz;
+                            const int faces_x = nearbox ? ((x == ulo[0]) | (x == uhi[0]) << 1) << 24 : 0;
+                            q[6] = __int_as_float((ix + iyz) | faces_yz | faces_x);
+                        }
+                        if (++ix == t.n) ix = 0;
+                    }
+                }
             }
             __syncwarp();
             if (lane < 4 && (listed & 1) && listed < PROJ_LIST) {  // odd count: the last pair's second cell repeats the first
