@@ -338,10 +338,11 @@ __global__ void k_wmultiband(WnTileView t, const float *p, size_t count, WnBands
 // Image grids: the 32 lanes of a warp are neighbouring pixels, a fraction of a tile cell apart, so they weigh almost
 // the same cells.  Per lane, eval3d_projected() spends most of its instructions FINDING its ~52 contributing cells (row
 // bounds for every row of its bounding box) and the lanes' loops diverge (ncu: 25 of 32 lanes active).  Here the warp
-// builds ONE candidate list cooperatively -- each lane tests one cell of the union bounding box per round against the
+// builds ONE candidate list cooperatively -- each lane takes one (y, z) row of the union bounding box and solves the
 // exact support region A (c - p) in (-1.5, 1.5)^3, A = I - n n^T / 2, widened by the extent of the warp's points and a
-// rounding slack, compacted with ballots in the reference's visiting order (z outer, x inner) into shared memory --
-// and then every lane evaluates every listed cell for its own point with the reference's arithmetic (cpp:239-260).  A
+// rounding slack, for the row's interval of x; the rows' counts are scanned across the warp so the cells land in shared
+// memory in the reference's visiting order (z outer, x inner) -- and then every lane evaluates every listed cell for
+// its own point with the reference's arithmetic (cpp:239-260), two cells per iteration on the packed FP32 pipe.  A
 // listed cell that is outside a lane's own reference box, or that the reference weighs with 0, contributes nothing, so
 // each lane adds its contributing cells in the reference's order: bit-identical to eval3d_projected().
 constexpr int PROJ_LIST = 192;                                 // candidate cells per warp (config 4 needs ~95)
