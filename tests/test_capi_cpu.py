@@ -292,3 +292,30 @@ def test_fold_plan_properties_on_random_lattices(monkeypatch):
                 if L < len(ax):
                     assert (e[L:] == e[:-L]).all(), (n, step, scale[b], L)
     assert folded_cases >= 10
+
+
+def test_projected_grid_kernel_has_no_contracted_packed_products():
+    """ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false (the scalar .rn forms are
+    never contracted).  k_proj_grid must keep the reference's separately rounded products (WaveletNoise.cpp:239-256), so
+    the only FFMA2 its SASS may hold are the harmless ones: a product added to zero, or a multiplication by 0.5 (exact,
+    so x * 0.5 + y rounds like fl(x * 0.5) + y)."""
+    import shutil
+    lib = wnpkg.load_sub("_lib")
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    inside, packed, bad = False, 0, []
+    for line in sass.splitlines():
+        if "Function :" in line:
+            inside = "k_proj_grid" in line
+            continue
+        if not inside:
+            continue
+        packed += bool(re.search(r"\bF(ADD|MUL)2\b", line))
+        if re.search(r"\bFFMA2\b", line):
+            ops = line.split("FFMA2", 1)[1].split(";")[0]
+            if not (re.search(r",\s*-?0\.5\s*,", ops) or re.search(r",\s*RZ(\.F32)?\s*$", ops.strip())):
+                bad.append(line.strip())
+    assert packed >= 40, "k_proj_grid no longer uses the packed FP32 pipe"
+    assert not bad, "contracted packed product in k_proj_grid:\n" + "\n".join(bad[:5])
