@@ -1533,14 +1533,15 @@ int launch_rep(WnTileView t, const WnTabs &tabs, int nx, int ny, int nk, float *
 }
 
 // Replica kernel for a lattice window with one or two direct bands.  Returns kernels launched, 0 when the window does
-// not qualify (the caller falls back to k_mb3d_col4), -1 on a launch error.
+// not qualify (the caller falls back to k_mb3d_col4), -1 on a launch error.  dry: launch nothing, return 1 where a
+// real call would launch.
 // Knobs (A/B runs): WN_REP=0 off, "11" / "12" / "22" = at most that many replicas along x and y (default "22");
 // WN_REP_YPW=1|4 thread mapping (NB = 1 only); WN_REP_TMA=0|1 period-block ring; WN_REP_SHARE=0: no shared bands;
 // WN_REP_BY=16: 128 x 16 x 32 bricks, 512 threads, one CTA per SM with an 8-plane ring (measured 0.843 ms against
 // 0.830 ms for the default two 8-row CTAs per SM on config 3: fewer X-pass rows, but the prologue is no longer hidden
 // behind a second CTA).
 int rep_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsigned char *rows, int k0, int nx, int ny, int nk,
-             const WnBands &b, WnFold fold, float *out, cudaStream_t st)
+             const WnBands &b, WnFold fold, float *out, cudaStream_t st, bool dry = false)
 {
     const int nb = b.nbands;
     if (nb < 1 || nb > 2 || nx % 4 != 0 || (fold.P && fold.Lx % 4 != 0)) return 0;
@@ -1596,6 +1597,7 @@ int rep_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsigned
         const size_t smem = ring_bytes + (size_t)max_rows * (128 * sizeof(float) + sizeof(int)) +
                             (size_t)nb * (128 + by + 32) * sizeof(float4) + 64;
         if (smem > (size_t)(by == 8 ? 113 : 226) * 1024) continue;
+        if (dry) return 1;                                     // the caller only asks whether this window streams
         CUtensorMap pmap;
         std::memset(&pmap, 0, sizeof(pmap));
         tma = tma && fold.P && fold.Lx % 128 == 0 && fold.Ly % by == 0 && fold.Lz % 4 == 0 && fold.kphase % 4 == 0 &&
@@ -1670,6 +1672,33 @@ int brick_pass(WnTileView t, const WnTabs &tabs, const HostAxes &h, const unsign
 #undef WN_COL4_CASE
             return b.nbands == 1 ? launch_col4<1, 8>(t, tabs, nx, ny, nk, out, plan, fold, st)
                                  : launch_col4<2, 8>(t, tabs, nx, ny, nk, out, plan, fold, st);
+        }
+    }
+    // Three or more direct bands: the brick kernels below pay for every band's whole y-z footprint, while the lowest one
+    // or two bands usually still stream through k_mb3d_rep.  The canonical sum takes the bands from the highest scale
+    // down, so the upper bands can be evaluated first (recursively, same rule) and the lowest ones added on top IN PLACE:
+    // the second pass reads `out` as its period block (period = the window itself; a CTA's ring only ever reads planes
+    // of its own column ahead of the plane it writes).  Same operations in the same order: bit-identical to one pass.
+    // WN_SPLIT=0 turns it off (A/B runs).
+    if (pick < 0 && can4 && col4_on && b.nbands >= 3 && (ny + 7) / 8 <= 65535 && (nk + 31) / 32 <= 65535) {
+        const char *split_env = getenv("WN_SPLIT");
+        if (!split_env || atoi(split_env) != 0) {
+            const WnFold inplace = make_fold(out, nx, ny, nk, 0);
+            for (int m = 2; m >= 1; --m) {
+                WnBands low = b, up = b;
+                low.nbands = m;
+                up.nbands = b.nbands - m;
+                for (int i = 0; i < up.nbands; ++i) { up.scale[i] = b.scale[i + m]; up.weight[i] = b.weight[i + m]; }
+                if (rep_pass(t, tabs, h, rows, k0, nx, ny, nk, low, inplace, out, st, true) != 1) continue;
+                WnTabs uptabs = tabs, lowtabs = tabs;
+                uptabs.rowbits = tabs.rowbits >> (4 * m);
+                uptabs.nb = up.nbands;
+                lowtabs.nb = m;
+                const int r1 = brick_pass(t, uptabs, h, rows + m, k0, nx, ny, nk, up, fold, out, st);
+                if (r1 < 0) break;                             // nothing launched: go on with the unsplit kernels
+                const int r2 = rep_pass(t, lowtabs, h, rows, k0, nx, ny, nk, low, inplace, out, st);
+                return r2 > 0 ? r1 + r2 : -1;                  // -1: the caller recomputes the window by direct gathers
+            }
         }
     }
     if (pick >= kFirstShape4 && !can4) pick = -1;
