@@ -355,6 +355,50 @@ def test_projected_and_perlin_affine_grid_config4(wn, oracle, gpu_tiles, tiles12
     assert_bits(gp, oracle.perlin_points(oracle.perlin_perm(12345), P4.reshape(-1, 3)).reshape(80, 96), "perlin affine grid")
 
 
+def test_projected_grid_random_geometry(wn, oracle, gpu_tiles, tiles128):
+    """k_proj_grid builds one candidate-cell list per 8 x 4 pixel patch (row intervals of the support region) and evaluates
+    it two cells at a time on the packed FP32 pipe; which of its paths runs depends on the geometry.  Random planes with
+    pixel spacings from 0.004 to 1.7 tile cells (whole-box patches, patches whose lanes' boxes differ by one layer, by
+    more than one layer, and patches too incoherent for a list), normals on an axis, within 1e-6 / 1e-3 of one and generic,
+    origins up to 300 cells (and 1e5) from zero, image sizes that are not multiples of the patch, a power-of-two and a
+    non-power-of-two tile: every pixel BIT-EXACT against the oracle."""
+    f = np.float32
+    rs = np.random.RandomState(1234)
+    small = wn.WaveletNoise(30, 807)
+    small.generateNoiseTile3D()
+    small_coeffs = small.getNoiseCoefficients()
+    tiles = [(gpu_tiles[3], tiles128[3], 128), (small, small_coeffs, 30)]
+    case = 0
+    for spacing in (0.004, 0.03, 0.11, 0.3, 0.9, 1.7):
+        for kind in ("axis", "near6", "near3", "generic"):
+            case += 1
+            tile, coeffs, n = tiles[case % 2]
+            axis = np.eye(3)[rs.randint(0, 3)] * rs.choice([-1.0, 1.0])
+            if kind == "axis":
+                nv = axis
+            elif kind == "near6":
+                nv = axis + rs.normal(size=3) * 1e-6
+            elif kind == "near3":
+                nv = axis + rs.normal(size=3) * 1e-3
+            else:
+                nv = rs.normal(size=3)
+            nv = (nv / np.linalg.norm(nv)).astype(f)
+            a = rs.normal(size=3); a /= np.linalg.norm(a)
+            b = np.cross(a, rs.normal(size=3)); b /= np.linalg.norm(b)
+            e1, e2 = a.astype(f), b.astype(f)
+            mag = 1e5 if case % 7 == 0 else 300.0
+            origin = (rs.uniform(-1, 1, 3) * mag).astype(f)
+            nu, nv_rows = int(rs.randint(33, 90)), int(rs.randint(5, 40))
+            us = (np.arange(nu, dtype=f) * f(spacing)).astype(f)
+            vs = (np.arange(nv_rows, dtype=f) * f(spacing * 1.3)).astype(f)
+            pre, post = f(1.0), f(1.0) / np.sqrt(f(0.296))
+            got = tile.evaluate3DProjected_grid(origin, e1, us, e2, vs, nv, float(pre), float(post))
+            U, V = np.meshgrid(us, vs)
+            P = ((origin[None, None, :] + U[..., None] * e1) + V[..., None] * e2).astype(f) * pre
+            want = oracle.eval3d_projected_points(coeffs, n, P.reshape(-1, 3), nv, 1.0, post).reshape(nv_rows, nu)
+            assert_bits(got, want, f"case {case}: spacing {spacing}, normal {kind}, n {n}, |o| ~{mag:g}")
+
+
 def test_config4_full_size_8192_squared(wn, oracle, gpu_tiles, tiles128):
     """BASELINE config 4 at its full size: WProjectedNoise on the 8192^2 oblique plane and Perlin(12345) octave 4 on the
     same grid, device resident.  65 536 random pixels plus two full rows (first / last) and two full columns against
