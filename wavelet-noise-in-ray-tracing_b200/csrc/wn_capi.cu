@@ -912,10 +912,11 @@ extern "C" int wn_multiband3d_lattice(const wn_tile *t, const float *xs, int nx,
     // FAST + device output: the chain (parameter upload, axis tables, period blocks) goes to the side stream so it
     // overlaps the previous call's main kernel; WN_SIDE_CHAIN=0 keeps everything on the compute stream (A/B runs)
     static const bool side_env = [] { const char *e = getenv("WN_SIDE_CHAIN"); return !e || atoi(e) != 0; }();
-    // Measured on config 3 shards: 157 -> 147 us (1/8 of the volume), 291 -> 280 us (1/4), 575 -> 557 us (1/2), but
-    // 1.12 -> 1.14 ms for the whole 1024^3, where the chain is bandwidth- rather than latency-bound and only competes
-    // with the main kernel for DRAM: the side stream is used up to 2^29 samples per call.
-    size_t side_max = (size_t)1 << 29;
+    // Measured on config 3 shards: 157 -> 147 us (1/8 of the volume), 291 -> 280 us (1/4), 575 -> 557 us (1/2).  For the
+    // whole 1024^3 it cost 2 % in round 1 (1.12 -> 1.14 ms: the 512^3 period block made the chain bandwidth-bound); with
+    // the 256^3 / 128^3 chain of round 2 it is 0.825 -> 0.819 ms (profiles/r2_side_chain_full_size.log), so the side
+    // stream is used up to 2^30 samples per call.
+    size_t side_max = (size_t)1 << 30;
     if (const char *e = getenv("WN_SIDE_MAX_LOG2")) side_max = (size_t)1 << atoi(e);     // read per call (A/B runs)
     const bool use_side = mode == WN_EVAL_FAST && space == WN_DEVICE && side_env && total <= side_max;
     ParamWriter pw(c, use_side);
