@@ -296,8 +296,9 @@ def test_fold_plan_properties_on_random_lattices(monkeypatch):
 
 def test_projected_grid_kernel_has_no_contracted_packed_products():
     """ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false (the scalar .rn forms are
-    never contracted).  k_proj_grid must keep the reference's separately rounded products (WaveletNoise.cpp:239-256), so
-    the only FFMA2 its SASS may hold are the harmless ones: a product added to zero, or a multiplication by 0.5 (exact,
+    never contracted).  The projected-noise kernels (k_proj_grid, k_proj<points / grid>, k_wmultiband) must keep the
+    reference's separately rounded products (WaveletNoise.cpp:239-256), so the only FFMA2 their SASS may hold are the
+    harmless ones: a product added to zero, or a multiplication by 0.5 (exact,
     so x * 0.5 + y rounds like fl(x * 0.5) + y)."""
     import shutil
     lib = wnpkg.load_sub("_lib")
@@ -308,7 +309,7 @@ def test_projected_grid_kernel_has_no_contracted_packed_products():
     inside, packed, bad = False, 0, []
     for line in sass.splitlines():
         if "Function :" in line:
-            inside = "k_proj_grid" in line
+            inside = any(k in line for k in ("k_proj", "k_wmultiband"))     # every kernel that evaluates projected noise
             continue
         if not inside:
             continue
@@ -317,5 +318,5 @@ def test_projected_grid_kernel_has_no_contracted_packed_products():
             ops = line.split("FFMA2", 1)[1].split(";")[0]
             if not (re.search(r",\s*-?0\.5\s*,", ops) or re.search(r",\s*RZ(\.F32)?\s*$", ops.strip())):
                 bad.append(line.strip())
-    assert packed >= 40, "k_proj_grid no longer uses the packed FP32 pipe"
-    assert not bad, "contracted packed product in k_proj_grid:\n" + "\n".join(bad[:5])
+    assert packed >= 40, "the projected-noise kernels no longer use the packed FP32 pipe"
+    assert not bad, "contracted packed product in a projected-noise kernel:\n" + "\n".join(bad[:5])
