@@ -230,14 +230,19 @@ __device__ double perlin3(const int *p /* 512 ints, shared memory */, double x, 
 // The float selects of grad() are single ALU ops where the FP64 ones are two, and the arithmetic leaves the FP64 pipe.
 __device__ __forceinline__ float pfadef(float t) { return t * t * t * fmaf(t, fmaf(t, 6.0f, -15.0f), 10.0f); }
 __device__ __forceinline__ float plerpf(float t, float a, float b) { return fmaf(t, b - a, a); }
-__device__ __forceinline__ float pgradf(int hash, float x, float y, float z)
+// gradient of hash h as coefficients of (x, y, z): grad(h, x, y, z) = cx x + cy y + cz z with one coefficient 0
+__device__ __forceinline__ float4 pgrad_coeff(int hash)
 {
     const int h = hash & 15;
-    const float u = h < 8 ? x : y;
-    const float v = h < 4 ? y : ((h == 12 || h == 14) ? x : z);
-    return ((h & 1) == 0 ? u : -u) + ((h & 2) == 0 ? v : -v);
+    const float su = (h & 1) ? -1.0f : 1.0f, sv = (h & 2) ? -1.0f : 1.0f;
+    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+    if (h < 8) cx += su; else cy += su;
+    if (h < 4) cy += sv; else if (h == 12 || h == 14) cx += sv; else cz += sv;
+    return make_float4(cx, cy, cz, 0.0f);
 }
-__device__ float perlin3f(const int *p, float x, float y, float z)
+// fast mode on image grids and batches: g[i] = pgrad_coeff(p[i]) (512 entries, built per CTA), so a corner is one
+// 16-byte shared-memory read and three FMAs instead of an integer lookup and nine selects
+__device__ float perlin3f_table(const int *p, const float4 *g, float x, float y, float z)
 {
     const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
     const int X = (int)fx & 255, Y = (int)fy & 255, Z = (int)fz & 255;
@@ -246,11 +251,12 @@ __device__ float perlin3f(const int *p, float x, float y, float z)
     const int A = p[X] + Y, AA = p[A] + Z, AB = p[A + 1] + Z;
     const int B = p[X + 1] + Y, BA = p[B] + Z, BB = p[B + 1] + Z;
     const float x1 = x - 1.0f, y1 = y - 1.0f, z1 = z - 1.0f;
+    auto dot = [](const float4 c, float a, float b, float d) { return fmaf(c.z, d, fmaf(c.y, b, c.x * a)); };
     return plerpf(w,
-        plerpf(v, plerpf(u, pgradf(p[AA], x, y, z),      pgradf(p[BA], x1, y, z)),
-                  plerpf(u, pgradf(p[AB], x, y1, z),     pgradf(p[BB], x1, y1, z))),
-        plerpf(v, plerpf(u, pgradf(p[AA + 1], x, y, z1), pgradf(p[BA + 1], x1, y, z1)),
-                  plerpf(u, pgradf(p[AB + 1], x, y1, z1), pgradf(p[BB + 1], x1, y1, z1))));
+        plerpf(v, plerpf(u, dot(g[AA], x, y, z),      dot(g[BA], x1, y, z)),
+                  plerpf(u, dot(g[AB], x, y1, z),     dot(g[BB], x1, y1, z))),
+        plerpf(v, plerpf(u, dot(g[AA + 1], x, y, z1), dot(g[BA + 1], x1, y, z1)),
+                  plerpf(u, dot(g[AB + 1], x, y1, z1), dot(g[BB + 1], x1, y1, z1))));
 }
 
 // ---- coordinate generators -------------------------------------------------------------------------
@@ -264,18 +270,33 @@ __device__ __forceinline__ void coord(const WnPointsAoS &c, size_t s, float p[3]
 #pragma unroll
     for (int i = 0; i < 3; ++i) p[i] = FMUL(__ldg(c.p + s * 3 + i), c.pre);
 }
+// s = q * n + r.  Sample indices below 2^32 (every configuration in BASELINE.json) take a 32-bit division: the 64-bit
+// one is a ~70-instruction sequence, a sixth of the Perlin kernel.
+__device__ __forceinline__ void split_index(size_t s, int n, size_t &q, size_t &r)
+{
+    if (s <= 0xffffffffull) {
+        const unsigned s32 = (unsigned)s, q32 = s32 / (unsigned)n;
+        q = q32;
+        r = s32 - q32 * (unsigned)n;
+    } else {
+        q = s / (size_t)n;
+        r = s - q * (size_t)n;
+    }
+}
 __device__ __forceinline__ void coord(const WnLattice &c, size_t s, float p[3])
 {
-    const size_t row = s / c.nx;
-    p[0] = __ldg(c.xs + (s - row * c.nx));
-    const size_t k = row / c.ny;
-    p[1] = __ldg(c.ys + (row - k * c.ny));
+    size_t row, i, k, j;
+    split_index(s, c.nx, row, i);
+    p[0] = __ldg(c.xs + i);
+    split_index(row, c.ny, k, j);
+    p[1] = __ldg(c.ys + j);
     p[2] = c.zs ? __ldg(c.zs + k) : 0.0f;
 }
 __device__ __forceinline__ void coord(const WnAffine &c, size_t s, float p[3])
 {
-    const size_t j = s / c.nu;
-    const float u = __ldg(c.us + (s - j * c.nu)), v = __ldg(c.vs + j);
+    size_t j, i;
+    split_index(s, c.nu, j, i);
+    const float u = __ldg(c.us + i), v = __ldg(c.vs + j);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
         p[i] = FMUL(FADD(FADD(c.o[i], FMUL(u, c.e1[i])), FMUL(v, c.e2[i])), c.pre);
@@ -597,12 +618,16 @@ template <class C, bool FAST>
 __global__ void k_perlin(const int32_t *perm, C c, size_t first, size_t count, float *out)
 {
     __shared__ int sp[512];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) sp[i] = perm[i];
+    __shared__ float4 sg[FAST ? 512 : 1];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        sp[i] = perm[i];
+        if (FAST) sg[i] = pgrad_coeff(perm[i]);
+    }
     __syncthreads();
     WN_TID_OR_RETURN(count);
     float p[3];
     coord(c, first + s, p);
-    if (FAST) out[s] = perlin3f(sp, p[0], p[1], p[2]);
+    if (FAST) out[s] = perlin3f_table(sp, sg, p[0], p[1], p[2]);
     else out[s] = (float)perlin3(sp, (double)p[0], (double)p[1], (double)p[2]);
 }
 // double coordinates in, double noise out: PerlinNoise::noise(double, double, double) as declared
